@@ -1,0 +1,159 @@
+/*
+ * foto_b200.h -- C ABI of libfoto_b200.so: the two dense-grid optical-flow solvers of
+ * thomasjacumin/optical-flow-optimal-transport as hand-written sm_100a CUDA.
+ *
+ * The reference is pure Python and has no FFI of its own; each entry point below replaces the
+ * reference function named beside it (file:line in the reference repository) and is what a
+ * ctypes binding in the reference's modules would call (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - float64 everywhere, C-contiguous.  Flat index k = n*P + y*Nx + x (x fastest), P = Nx*Ny,
+ *     N = Nt*P; 3-component fields are concatenated [c0 | c1 | c2] (reference layout,
+ *     benamou_brenier.py:119-121,191-192).  Note Nx = image width, Ny = image height.
+ *   - "host" entry points take host pointers, are blocking, and own all device traffic
+ *     (H2D, kernels, D2H).  "_dev" entry points take device pointers of the context's device
+ *     and are blocking too (the outer loop's stopping rule is evaluated on the host).
+ *   - Every function returns FOTO_OK (0) or a negative FOTO_ERR_* code; foto_last_error()
+ *     gives a thread-local message.  There is NO CPU fallback: without a usable CUDA device
+ *     every compute entry point fails with FOTO_ERR_NODEV / FOTO_ERR_CUDA.
+ *   - Thread safety: a foto_ctx must not be used from two threads at once; different contexts
+ *     (same or different devices) are independent.  The host entry points use one lazily
+ *     created context per (thread, current CUDA device).
+ */
+#ifndef FOTO_B200_H
+#define FOTO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FOTO_OK                 0
+#define FOTO_ERR_ARG           -1   /* bad argument (sizes < 2, NULL, unknown id)              */
+#define FOTO_ERR_CUDA          -2   /* CUDA runtime error, message in foto_last_error()        */
+#define FOTO_ERR_NODEV         -3   /* no CUDA device / device is not sm_100                   */
+#define FOTO_ERR_BREAKDOWN     -4   /* CG breakdown (reference: RuntimeError, bb.py:88-89)     */
+#define FOTO_ERR_TIMEOUT       -5   /* grid-barrier watchdog fired inside a persistent kernel  */
+#define FOTO_ERR_NOTIMPL       -6   /* unknown boundary condition / operator (NotImplementedError) */
+
+/* Poisson back-ends for stepA (parity trap #1) */
+#define FOTO_POISSON_CG_PARITY  0   /* scipy.sparse.linalg.cg recurrence, rtol 1e-6, maxiter 1000, x0 = 0 */
+#define FOTO_POISSON_CG_TIGHT   1   /* same recurrence, rtol 1e-13, maxiter 100000 ("tight" oracle)      */
+
+/* operator ids for foto_op_apply (reference operators.py) */
+#define FOTO_OP_GRAD_ST         0   /* operators.py:114-127   N  -> 3N */
+#define FOTO_OP_DIV_ST          1   /* operators.py:129-142   3N -> N  */
+#define FOTO_OP_LAPLACIAN_ST    2   /* operators.py:144-157   N  -> N  */
+#define FOTO_OP_GRAD            3   /* operators.py:160-169   P  -> 2P */
+#define FOTO_OP_DIV             4   /* operators.py:182-191   2P -> P  */
+#define FOTO_OP_GRAD_FORWARD    5   /* operators.py:171-180   P  -> 2P */
+/* 1-D builder ids for foto_op_apply_1d (operators.py:5-110) */
+#define FOTO_1D_FORWARD_WEIRD   0
+#define FOTO_1D_BACKWARD_WEIRD  1
+#define FOTO_1D_CENTRAL_WEIRD   2
+#define FOTO_1D_CENTRAL         3
+#define FOTO_1D_FORWARD         4
+#define FOTO_1D_BACKWARD        5
+#define FOTO_1D_LAP             6
+#define FOTO_BC_N               0
+#define FOTO_BC_D               1
+
+typedef struct foto_ctx foto_ctx;
+
+/* per-context counters, reset by foto_ctx_reset_stats().  Times are CUDA-event milliseconds
+ * measured on the context's stream, accumulated only while profiling is on. */
+typedef struct foto_stats {
+    long long launches;        /* kernels of this library launched                       */
+    long long cg_launches;     /* launches of the persistent CG kernel (one per stepA)   */
+    long long cg_iterations;   /* CG iterations summed over those launches               */
+    long long cg_cells;        /* sum over launches of (iterations * N)                  */
+    double    cg_ms;           /* device time inside the CG kernel                       */
+    double    rhs_ms;          /* K1                                                     */
+    double    prox_ms;         /* K3                                                     */
+    double    flow_ms;         /* K4                                                     */
+    long long rhs_cells, prox_cells;
+    long long gn_launches, gn_iterations, gn_pixels;   /* GN persistent PCG kernel       */
+    double    gn_ms;
+    int       cg_variant;      /* 0 streaming (L2/HBM), 1 on-chip resident               */
+    int       reserved;
+} foto_stats;
+
+const char *foto_last_error(void);
+int  foto_version(void);
+int  foto_device_count(void);                               /* < 0 on error */
+
+/* ---- contexts (device-resident API) ------------------------------------------------ */
+int  foto_ctx_create(int device, foto_ctx **out);
+void foto_ctx_destroy(foto_ctx *ctx);
+int  foto_ctx_device(const foto_ctx *ctx);
+int  foto_ctx_set_profiling(foto_ctx *ctx, int on);         /* CUDA-event timing of K1..K4 */
+int  foto_ctx_reset_stats(foto_ctx *ctx);
+int  foto_ctx_get_stats(foto_ctx *ctx, foto_stats *out);
+int  foto_ctx_set_cg_variant(foto_ctx *ctx, int variant);   /* -1 auto, 0 streaming, 1 on-chip */
+
+/* benamou_brenier.solve (benamou_brenier.py:151-271) on device buffers.
+ * d_rho0, d_rhoT: P doubles; d_u, d_v, d_m: P doubles (outputs).
+ * crit_trace[max_it], cg_iters[max_it] (host, may be NULL): per outer iteration the stopping
+ * criterion printed at benamou_brenier.py:252 and the inner CG iteration count;
+ * cg_info[max_it] (host, may be NULL): scipy's `info` (0 converged, maxiter otherwise -> the
+ * WARNING of benamou_brenier.py:86-87).  *n_outer = outer iterations performed. */
+int  foto_solve_dev(foto_ctx *ctx, const double *d_rho0, const double *d_rhoT,
+                    int Nt, int Nx, int Ny, double r, double tol, double eps, int max_it,
+                    int poisson_backend, double *d_u, double *d_v, double *d_m,
+                    double *crit_trace, int *n_outer, int *cg_iters, int *cg_info);
+
+/* classical.GLLOpticalFlow.assemble + process (classical.py:68-130) on device buffers.
+ * The direct SuperLU solve is replaced by a matrix-free Jacobi-preconditioned CG run until
+ * ||r|| <= rtol ||b|| (rtol <= 0 selects 1e-13; max_it <= 0 selects 20000). */
+int  foto_gn_solve_dev(foto_ctx *ctx, const double *d_f1, const double *d_f2, int w, int h,
+                       double alpha, double lambda, double rtol, int max_it,
+                       double *d_u, double *d_v, double *d_m, int *iters, int *info);
+
+/* ---- host-buffer API (what the reference's Python modules bind) ------------------- */
+/* benamou_brenier.solve, benamou_brenier.py:151 */
+int  foto_solve(const double *rho0, const double *rhoT, int Nt, int Nx, int Ny,
+                double r, double tol, double eps, int max_it, int poisson_backend,
+                double *u, double *v, double *m,
+                double *crit_trace, int *n_outer, int *cg_iters, int *cg_info);
+/* benamou_brenier.stepB, benamou_brenier.py:93 : p[3N] -> q[3N] */
+int  foto_stepB(const double *p, int Nt, int Nx, int Ny, double *q);
+/* benamou_brenier.solve_benamou_brenier_step, benamou_brenier.py:26 (matrix A = -r L + r eps I
+ * and div_st are implied by r, eps and the grid; dt = dx = dy = 1 as in solve()). */
+int  foto_stepA(const double *mu, const double *q, const double *rho0, const double *rhoT,
+                double r, double eps, int Nt, int Nx, int Ny, int poisson_backend,
+                double *phi, int *cg_iters, int *cg_info);
+/* right-hand side of stepA alone (benamou_brenier.py:64-82) */
+int  foto_rhs(const double *mu, const double *q, const double *rho0, const double *rhoT,
+              double r, int Nt, int Nx, int Ny, double *F);
+/* utils.opticalflow_from_benamoubrenier, utils.py:148 with grad(...,'N'), div(...,'D') */
+int  foto_flow_from_phi(const double *phi, int Nt, int Nx, int Ny, double *u, double *v, double *m);
+/* operators.* applied matrix-free: out = Op(in) or Op^T(in) */
+int  foto_op_apply(int op_id, int bc, int Nt, int Nx, int Ny, double dt, double dx, double dy,
+                   int transpose, const double *in, double *out);
+/* 1-D builders of operators.py:5-110 as (lo, di, up) rows; host-only helper (no GPU) */
+int  foto_tri_coeffs(int kind, int n, double h, int bc, double *lo, double *di, double *up);
+/* classical.GLLOpticalFlow.assemble().process(), classical.py:68-130 */
+int  foto_gn_solve(const double *f1, const double *f2, int w, int h, double alpha, double lambda,
+                   double rtol, int max_it, double *u, double *v, double *m, int *iters, int *info);
+/* A @ x and b of the GN system (classical.py:106-110), matrix-free; x, y, b: 3P doubles */
+int  foto_gn_system(const double *f1, const double *f2, int w, int h, double alpha, double lambda,
+                    const double *x, double *y, double *b);
+/* utils.apply_opticalflow, utils.py:186 ; m may be NULL */
+int  foto_warp_apply(const double *f1, const double *u, const double *v, int w, int h,
+                     const double *m_or_null, double *out);
+
+/* Many independent pairs of one shape, sharded over devices by a work queue (one host thread
+ * per device, no collective).  rho0s/rhoTs: n_pairs*P doubles,
+ * us/vs/ms: n_pairs*P doubles; n_outer[n_pairs]; device_ids[n_dev] (NULL: devices 0..n_dev-1). */
+int  foto_solve_batch(int n_pairs, const double *rho0s, const double *rhoTs, int Nt, int Nx, int Ny,
+                      double r, double tol, double eps, int max_it, int poisson_backend,
+                      const int *device_ids, int n_dev,
+                      double *us, double *vs, double *ms, int *n_outer);
+int  foto_gn_solve_batch(int n_pairs, const double *f1s, const double *f2s, int w, int h,
+                         double alpha, double lambda, double rtol, int max_it,
+                         const int *device_ids, int n_dev,
+                         double *us, double *vs, double *ms, int *iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOTO_B200_H */

@@ -1,0 +1,718 @@
+// api.cu -- C ABI of libfoto_b200.so (include/foto_b200.h): contexts, workspaces, the outer
+// ALG2 loop of benamou_brenier.solve, the GN driver, operator application and the per-device
+// work-queue batch driver.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <atomic>
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+
+#include "foto_kernels.cuh"
+
+namespace foto {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace foto
+
+using namespace foto;
+
+// ------------------------------------------------------------------------------- context
+struct DevResult {          // written by kernels, copied to the pinned mirror once per outer step
+    double crit[2];         // numerator / denominator sums of the stopping criterion
+    int cg_iters, cg_info;  // scipy-style (iterations, info)
+    int error, pad;
+};
+
+enum Cat { CAT_RHS = 0, CAT_CG, CAT_PROX, CAT_FLOW, CAT_GN, CAT_COUNT };
+
+struct foto_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    char *ws = nullptr;     size_t ws_bytes = 0;      // solver workspace
+    char *io = nullptr;     size_t io_bytes = 0;      // staging for the host-buffer API
+    unsigned int *sync_counter = nullptr;
+    double *sync_partials = nullptr;
+    double *prox_partials = nullptr;
+    DevResult *d_res = nullptr;
+    DevResult *h_res = nullptr;                       // pinned
+    int cg_grid = 0, cg_block = 0, gn_grid = 0, gn_block = 0;
+    int cg_variant = -1;
+    bool profiling = false;
+    foto_stats stats{};
+    std::vector<cudaEvent_t> ev_pool;
+    struct Span { cudaEvent_t a, b; int cat; };
+    std::vector<Span> spans;
+    cudaEvent_t open_a = nullptr; int open_cat = -1;
+};
+
+static const int kProxMaxBlocks = 148 * 8;
+
+static int ctx_bind(const foto_ctx *c)
+{
+    CUDA_TRY(cudaSetDevice(c->device));
+    return FOTO_OK;
+}
+
+static int ensure(char **buf, size_t *have, size_t need)
+{
+    if (*have >= need) return FOTO_OK;
+    if (*buf) { CUDA_TRY(cudaFree(*buf)); *buf = nullptr; *have = 0; }
+    need = (need + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+    CUDA_TRY(cudaMalloc((void **)buf, need));
+    *have = need;
+    return FOTO_OK;
+}
+
+struct Carver {             // 256-byte aligned sub-allocation of a workspace
+    char *base; size_t off = 0;
+    explicit Carver(char *b) : base(b) {}
+    double *take(size_t n) { double *p = (double *)(base + off); off += (n * sizeof(double) + 255) & ~size_t(255); return p; }
+    static size_t bytes(size_t n) { return (n * sizeof(double) + 255) & ~size_t(255); }
+};
+
+static void prof_begin(foto_ctx *c, int cat)
+{
+    if (!c->profiling) return;
+    cudaEvent_t e;
+    if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); } else cudaEventCreate(&e);
+    cudaEventRecord(e, c->stream);
+    c->open_a = e; c->open_cat = cat;
+}
+
+static void prof_end(foto_ctx *c)
+{
+    if (!c->profiling || !c->open_a) return;
+    cudaEvent_t e;
+    if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); } else cudaEventCreate(&e);
+    cudaEventRecord(e, c->stream);
+    c->spans.push_back({c->open_a, e, c->open_cat});
+    c->open_a = nullptr;
+}
+
+static void prof_resolve(foto_ctx *c)      // call after the stream has been synchronised
+{
+    for (auto &s : c->spans) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s.a, s.b);
+        switch (s.cat) {
+        case CAT_RHS: c->stats.rhs_ms += ms; break;
+        case CAT_CG: c->stats.cg_ms += ms; break;
+        case CAT_PROX: c->stats.prox_ms += ms; break;
+        case CAT_FLOW: c->stats.flow_ms += ms; break;
+        case CAT_GN: c->stats.gn_ms += ms; break;
+        }
+        c->ev_pool.push_back(s.a); c->ev_pool.push_back(s.b);
+    }
+    c->spans.clear();
+}
+
+extern "C" const char *foto_last_error(void) { return g_err; }
+extern "C" int foto_version(void) { return 100; }
+
+extern "C" int foto_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e)); return FOTO_ERR_NODEV; }
+    return n;
+}
+
+extern "C" int foto_ctx_create(int device, foto_ctx **out)
+{
+    if (!out) { set_error("foto_ctx_create: out is NULL"); return FOTO_ERR_ARG; }
+    *out = nullptr;
+    int n = foto_device_count();
+    if (n <= 0) { if (n == 0) set_error("no CUDA device: libfoto_b200 has no CPU fallback"); return FOTO_ERR_NODEV; }
+    if (device < 0 || device >= n) { set_error("device %d out of range (have %d)", device, n); return FOTO_ERR_ARG; }
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; libfoto_b200 is built for sm_100a only", device, prop.major, prop.minor);
+        return FOTO_ERR_NODEV;
+    }
+    foto_ctx *c = new foto_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    int rc = [&]() -> int {
+        CUDA_TRY(cudaSetDevice(device));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaMalloc((void **)&c->sync_counter, 256));
+        CUDA_TRY(cudaMalloc((void **)&c->sync_partials, sizeof(double) * 2 * kMaxVals * kMaxBlocks));
+        CUDA_TRY(cudaMalloc((void **)&c->prox_partials, sizeof(double) * 2 * kProxMaxBlocks));
+        CUDA_TRY(cudaMalloc((void **)&c->d_res, sizeof(DevResult)));
+        CUDA_TRY(cudaMemset(c->d_res, 0, sizeof(DevResult)));
+        CUDA_TRY(cudaMemset(c->sync_counter, 0, 256));
+        CUDA_TRY(cudaMallocHost((void **)&c->h_res, sizeof(DevResult)));
+        FOTO_TRY(cg_stream_config(device, &c->cg_grid, &c->cg_block));
+        FOTO_TRY(gn_pcg_config(device, &c->gn_grid, &c->gn_block));
+        return FOTO_OK;
+    }();
+    if (rc != FOTO_OK) { foto_ctx_destroy(c); return rc; }
+    *out = c;
+    return FOTO_OK;
+}
+
+extern "C" void foto_ctx_destroy(foto_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    cudaFree(c->ws); cudaFree(c->io); cudaFree(c->sync_counter); cudaFree(c->sync_partials);
+    cudaFree(c->prox_partials); cudaFree(c->d_res);
+    if (c->h_res) cudaFreeHost(c->h_res);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int foto_ctx_device(const foto_ctx *c) { return c ? c->device : FOTO_ERR_ARG; }
+extern "C" int foto_ctx_set_profiling(foto_ctx *c, int on) { if (!c) return FOTO_ERR_ARG; c->profiling = on != 0; return FOTO_OK; }
+extern "C" int foto_ctx_reset_stats(foto_ctx *c) { if (!c) return FOTO_ERR_ARG; c->stats = foto_stats{}; return FOTO_OK; }
+extern "C" int foto_ctx_get_stats(foto_ctx *c, foto_stats *out) { if (!c || !out) return FOTO_ERR_ARG; *out = c->stats; return FOTO_OK; }
+extern "C" int foto_ctx_set_cg_variant(foto_ctx *c, int v)
+{
+    if (!c || v < -1 || v > 1) { set_error("cg variant must be -1, 0 or 1"); return FOTO_ERR_ARG; }
+    c->cg_variant = v;
+    return FOTO_OK;
+}
+
+// ------------------------------------------------------------------------------- helpers
+static int make_dims(int Nt, int Nx, int Ny, Dims *d)
+{
+    if (Nt < 2 || Nx < 2 || Ny < 2) { set_error("grid must be at least 2 in every direction (Nt=%d Nx=%d Ny=%d)", Nt, Nx, Ny); return FOTO_ERR_ARG; }
+    unsigned long long P = (unsigned long long)Nx * Ny, N = P * Nt;
+    if (3ull * N >= (1ull << 32)) { set_error("grid too large for 32-bit cell indices (3N = %llu)", 3ull * N); return FOTO_ERR_ARG; }
+    d->Nt = Nt; d->Ny = Ny; d->Nx = Nx; d->P = (unsigned int)P; d->N = (unsigned int)N;
+    return FOTO_OK;
+}
+
+static int fetch_result(foto_ctx *c)
+{
+    CUDA_TRY(cudaMemcpyAsync(c->h_res, c->d_res, sizeof(DevResult), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->h_res->error) {
+        cudaMemsetAsync(&c->d_res->error, 0, sizeof(int), c->stream);
+        set_error("grid-barrier watchdog fired inside a persistent kernel");
+        return FOTO_ERR_TIMEOUT;
+    }
+    return FOTO_OK;
+}
+
+// One Poisson solve A phi = F on device buffers.  work: 4N doubles (r, p0, p1, q).
+static int run_cg(foto_ctx *c, const Dims &d, const double *F, double *phi, double *work, double r, double eps,
+                  int backend)
+{
+    CgArgs a;
+    a.b = F; a.x = phi;
+    a.r = work; a.p0 = work + d.N; a.p1 = work + 2ull * d.N; a.q = work + 3ull * d.N;
+    a.Nt = d.Nt; a.Ny = d.Ny; a.Nx = d.Nx;
+    a.rcoef = r; a.eps = eps;
+    if (backend == FOTO_POISSON_CG_PARITY) { a.rtol = 1e-6; a.maxiter = 1000; }          // benamou_brenier.py:85
+    else if (backend == FOTO_POISSON_CG_TIGHT) { a.rtol = 1e-13; a.maxiter = 100000; }
+    else { set_error("unknown Poisson back-end %d", backend); return FOTO_ERR_ARG; }
+    a.sync.counter = c->sync_counter; a.sync.partials = c->sync_partials; a.sync.error = &c->d_res->error;
+    a.out = &c->d_res->cg_iters;
+    bool onchip = c->cg_variant == 1 || (c->cg_variant == -1 && cg_onchip_fits(c->device, d.Nt, d.Ny, d.Nx));
+    prof_begin(c, CAT_CG);
+    if (onchip) FOTO_TRY(launch_cg_onchip(c->stream, a, c->device));
+    else FOTO_TRY(launch_cg_stream(c->stream, a, c->cg_grid, c->cg_block));
+    prof_end(c);
+    c->stats.cg_variant = onchip ? 1 : 0;
+    c->stats.launches++; c->stats.cg_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return FOTO_OK;
+}
+
+static size_t solve_ws_bytes(const Dims &d)
+{
+    return 2 * Carver::bytes(3ull * d.N) + 2 * Carver::bytes(d.N) + Carver::bytes(4ull * d.N);
+}
+
+// ------------------------------------------------------------------------------- FOTO solve
+extern "C" int foto_solve_dev(foto_ctx *c, const double *d_rho0, const double *d_rhoT, int Nt, int Nx, int Ny,
+                              double r, double tol, double eps, int max_it, int backend, double *d_u, double *d_v,
+                              double *d_m, double *crit_trace, int *n_outer, int *cg_iters, int *cg_info)
+{
+    if (!c || !d_rho0 || !d_rhoT || !d_u || !d_v || !d_m) { set_error("foto_solve_dev: NULL argument"); return FOTO_ERR_ARG; }
+    if (max_it < 1) { set_error("max_it must be >= 1"); return FOTO_ERR_ARG; }
+    Dims d;
+    FOTO_TRY(make_dims(Nt, Nx, Ny, &d));
+    FOTO_TRY(ctx_bind(c));
+    FOTO_TRY(ensure(&c->ws, &c->ws_bytes, solve_ws_bytes(d)));
+    Carver cv(c->ws);
+    double *mu = cv.take(3ull * d.N), *q = cv.take(3ull * d.N), *F = cv.take(d.N), *phi = cv.take(d.N);
+    double *work = cv.take(4ull * d.N);          // CG vectors r, p0, p1, q (contiguous, stride N)
+
+    launch_init_state(c->stream, d, d_rho0, d_rhoT, mu, q);
+    c->stats.launches++;
+    double crit = -1.0;
+    int outer = 0;
+    for (int it = 0; it < max_it; it++) {
+        prof_begin(c, CAT_RHS);
+        launch_rhs(c->stream, d, mu, q, d_rho0, d_rhoT, r, F);                 // stepA, right-hand side
+        prof_end(c);
+        FOTO_TRY(run_cg(c, d, F, phi, work, r, eps, backend));                 // stepA, Poisson solve
+        prof_begin(c, CAT_PROX);
+        int blocks = launch_prox_dual(c->stream, d, phi, mu, q, r, c->prox_partials, kProxMaxBlocks);   // stepB + stepC
+        launch_crit_final(c->stream, c->prox_partials, blocks, c->d_res->crit);
+        prof_end(c);
+        c->stats.launches += 3;
+        c->stats.rhs_cells += d.N; c->stats.prox_cells += d.N;
+        CUDA_TRY(cudaGetLastError());
+        FOTO_TRY(fetch_result(c));
+        c->stats.cg_iterations += c->h_res->cg_iters;
+        c->stats.cg_cells += (long long)c->h_res->cg_iters * d.N;
+        if (cg_iters) cg_iters[it] = c->h_res->cg_iters;
+        if (cg_info) cg_info[it] = c->h_res->cg_info;
+        const double prev = crit;
+        crit = std::sqrt(c->h_res->crit[0] / (c->h_res->crit[1] + 1e-10));     // benamou_brenier.py:251
+        if (crit_trace) crit_trace[it] = crit;
+        outer = it + 1;
+        if (crit <= tol) break;                                                // benamou_brenier.py:254
+        if (prev >= 0 && std::fabs(prev - crit) < 1e-5) break;                 // benamou_brenier.py:256-258
+    }
+    if (n_outer) *n_outer = outer;
+    prof_begin(c, CAT_FLOW);
+    launch_flow(c->stream, d, phi, d_u, d_v, d_m);
+    prof_end(c);
+    c->stats.launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    prof_resolve(c);
+    return FOTO_OK;
+}
+
+// ------------------------------------------------------------------------------- GN solve
+extern "C" int foto_gn_solve_dev(foto_ctx *c, const double *d_f1, const double *d_f2, int w, int h, double alpha,
+                                 double lambda, double rtol, int max_it, double *d_u, double *d_v, double *d_m,
+                                 int *iters, int *info)
+{
+    if (!c || !d_f1 || !d_f2 || !d_u || !d_v || !d_m) { set_error("foto_gn_solve_dev: NULL argument"); return FOTO_ERR_ARG; }
+    if (w < 2 || h < 2) { set_error("image must be at least 2x2"); return FOTO_ERR_ARG; }
+    unsigned long long P = (unsigned long long)w * h;
+    if (3ull * P >= (1ull << 31)) { set_error("image too large"); return FOTO_ERR_ARG; }
+    if (rtol <= 0) rtol = 1e-13;
+    if (max_it <= 0) max_it = 20000;
+    FOTO_TRY(ctx_bind(c));
+    FOTO_TRY(ensure(&c->ws, &c->ws_bytes, 2 * Carver::bytes(P) + 8 * Carver::bytes(3 * P)));
+    Carver cv(c->ws);
+    GnArgs a;
+    double *fx = cv.take(P), *fy = cv.take(P), *dinv = cv.take(3 * P), *b = cv.take(3 * P);
+    a.fx = fx; a.fy = fy; a.f2 = d_f2; a.dinv = dinv; a.b = b;
+    a.x = cv.take(3 * P); a.r = cv.take(3 * P); a.z = cv.take(3 * P);
+    a.p0 = cv.take(3 * P); a.p1 = cv.take(3 * P); a.q = cv.take(3 * P);
+    a.w = w; a.h = h; a.alpha = alpha; a.lam = lambda; a.rtol = rtol; a.maxiter = max_it;
+    a.sync.counter = c->sync_counter; a.sync.partials = c->sync_partials; a.sync.error = &c->d_res->error;
+    a.out = &c->d_res->cg_iters;
+    launch_gn_coeffs(c->stream, w, h, d_f1, d_f2, alpha, lambda, fx, fy, dinv, b);
+    prof_begin(c, CAT_GN);
+    FOTO_TRY(launch_gn_pcg(c->stream, a, c->gn_grid, c->gn_block));
+    prof_end(c);
+    c->stats.launches += 2; c->stats.gn_launches++;
+    CUDA_TRY(cudaMemcpyAsync(d_u, a.x, P * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_v, a.x + P, P * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_m, a.x + 2 * P, P * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaGetLastError());
+    FOTO_TRY(fetch_result(c));
+    prof_resolve(c);
+    c->stats.gn_iterations += c->h_res->cg_iters;
+    c->stats.gn_pixels += (long long)c->h_res->cg_iters * (long long)P;
+    if (iters) *iters = c->h_res->cg_iters;
+    if (info) *info = c->h_res->cg_info;
+    return FOTO_OK;
+}
+
+// ------------------------------------------------------------------------------- host API
+static std::mutex g_ctx_mutex;
+static std::map<std::pair<std::thread::id, int>, foto_ctx *> g_ctx;
+
+static int default_ctx(foto_ctx **out)
+{
+    int n = foto_device_count();
+    if (n <= 0) { if (n == 0) set_error("no CUDA device: libfoto_b200 has no CPU fallback"); return FOTO_ERR_NODEV; }
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_ctx_mutex);
+    auto key = std::make_pair(std::this_thread::get_id(), dev);
+    auto it = g_ctx.find(key);
+    if (it != g_ctx.end()) { *out = it->second; return FOTO_OK; }
+    foto_ctx *c = nullptr;
+    FOTO_TRY(foto_ctx_create(dev, &c));
+    g_ctx[key] = c;
+    *out = c;
+    return FOTO_OK;
+}
+
+struct IoPlan {             // host<->device staging of doubles through ctx->io
+    foto_ctx *c; size_t off = 0;
+    explicit IoPlan(foto_ctx *ctx) : c(ctx) {}
+    double *slot(size_t n) { double *p = (double *)(c->io + off); off += Carver::bytes(n); return p; }
+};
+
+static int h2d(foto_ctx *c, double *dst, const double *src, size_t n)
+{
+    CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return FOTO_OK;
+}
+static int d2h(foto_ctx *c, double *dst, const double *src, size_t n)
+{
+    CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return FOTO_OK;
+}
+
+static int solve_on_ctx(foto_ctx *c, const double *rho0, const double *rhoT, int Nt, int Nx, int Ny, double r,
+                        double tol, double eps, int max_it, int backend, double *u, double *v, double *m,
+                        double *crit_trace, int *n_outer, int *cg_iters, int *cg_info)
+{
+    if (!rho0 || !rhoT || !u || !v || !m) { set_error("foto_solve: NULL argument"); return FOTO_ERR_ARG; }
+    Dims d;
+    FOTO_TRY(make_dims(Nt, Nx, Ny, &d));
+    FOTO_TRY(ctx_bind(c));
+    FOTO_TRY(ensure(&c->io, &c->io_bytes, 5 * Carver::bytes(d.P)));
+    IoPlan io(c);
+    double *d0 = io.slot(d.P), *dT = io.slot(d.P), *du = io.slot(d.P), *dv = io.slot(d.P), *dm = io.slot(d.P);
+    FOTO_TRY(h2d(c, d0, rho0, d.P));
+    FOTO_TRY(h2d(c, dT, rhoT, d.P));
+    FOTO_TRY(foto_solve_dev(c, d0, dT, Nt, Nx, Ny, r, tol, eps, max_it, backend, du, dv, dm, crit_trace, n_outer,
+                            cg_iters, cg_info));
+    FOTO_TRY(d2h(c, u, du, d.P));
+    FOTO_TRY(d2h(c, v, dv, d.P));
+    FOTO_TRY(d2h(c, m, dm, d.P));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FOTO_OK;
+}
+
+extern "C" int foto_solve(const double *rho0, const double *rhoT, int Nt, int Nx, int Ny, double r, double tol,
+                          double eps, int max_it, int backend, double *u, double *v, double *m, double *crit_trace,
+                          int *n_outer, int *cg_iters, int *cg_info)
+{
+    foto_ctx *c = nullptr;
+    FOTO_TRY(default_ctx(&c));
+    return solve_on_ctx(c, rho0, rhoT, Nt, Nx, Ny, r, tol, eps, max_it, backend, u, v, m, crit_trace, n_outer,
+                        cg_iters, cg_info);
+}
+
+extern "C" int foto_stepB(const double *p, int Nt, int Nx, int Ny, double *q)
+{
+    if (!p || !q) { set_error("foto_stepB: NULL argument"); return FOTO_ERR_ARG; }
+    foto_ctx *c = nullptr;
+    FOTO_TRY(default_ctx(&c));
+    if (Nt < 1 || Nx < 1 || Ny < 1) { set_error("foto_stepB: empty grid"); return FOTO_ERR_ARG; }
+    unsigned long long N = (unsigned long long)Nt * Nx * Ny;
+    if (3ull * N >= (1ull << 32)) { set_error("grid too large"); return FOTO_ERR_ARG; }
+    FOTO_TRY(ctx_bind(c));
+    FOTO_TRY(ensure(&c->io, &c->io_bytes, 2 * Carver::bytes(3 * N)));
+    IoPlan io(c);
+    double *dp = io.slot(3 * N), *dq = io.slot(3 * N);
+    FOTO_TRY(h2d(c, dp, p, 3 * N));
+    launch_stepB(c->stream, (unsigned int)N, dp, dq);
+    c->stats.launches++;
+    CUDA_TRY(cudaGetLastError());
+    FOTO_TRY(d2h(c, q, dq, 3 * N));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FOTO_OK;
+}
+
+extern "C" int foto_rhs(const double *mu, const double *q, const double *rho0, const double *rhoT, double r, int Nt,
+                        int Nx, int Ny, double *F)
+{
+    if (!mu || !q || !rho0 || !rhoT || !F) { set_error("foto_rhs: NULL argument"); return FOTO_ERR_ARG; }
+    foto_ctx *c = nullptr;
+    FOTO_TRY(default_ctx(&c));
+    Dims d;
+    FOTO_TRY(make_dims(Nt, Nx, Ny, &d));
+    FOTO_TRY(ctx_bind(c));
+    FOTO_TRY(ensure(&c->io, &c->io_bytes, 2 * Carver::bytes(3ull * d.N) + 2 * Carver::bytes(d.P) + Carver::bytes(d.N)));
+    IoPlan io(c);
+    double *dmu = io.slot(3ull * d.N), *dq = io.slot(3ull * d.N), *d0 = io.slot(d.P), *dT = io.slot(d.P), *dF = io.slot(d.N);
+    FOTO_TRY(h2d(c, dmu, mu, 3ull * d.N)); FOTO_TRY(h2d(c, dq, q, 3ull * d.N));
+    FOTO_TRY(h2d(c, d0, rho0, d.P)); FOTO_TRY(h2d(c, dT, rhoT, d.P));
+    launch_rhs(c->stream, d, dmu, dq, d0, dT, r, dF);
+    c->stats.launches++;
+    CUDA_TRY(cudaGetLastError());
+    FOTO_TRY(d2h(c, F, dF, d.N));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FOTO_OK;
+}
+
+extern "C" int foto_stepA(const double *mu, const double *q, const double *rho0, const double *rhoT, double r,
+                          double eps, int Nt, int Nx, int Ny, int backend, double *phi, int *cg_iters, int *cg_info)
+{
+    if (!mu || !q || !rho0 || !rhoT || !phi) { set_error("foto_stepA: NULL argument"); return FOTO_ERR_ARG; }
+    foto_ctx *c = nullptr;
+    FOTO_TRY(default_ctx(&c));
+    Dims d;
+    FOTO_TRY(make_dims(Nt, Nx, Ny, &d));
+    FOTO_TRY(ctx_bind(c));
+    FOTO_TRY(ensure(&c->io, &c->io_bytes, 2 * Carver::bytes(3ull * d.N) + 2 * Carver::bytes(d.P) + 2 * Carver::bytes(d.N)));
+    FOTO_TRY(ensure(&c->ws, &c->ws_bytes, 4ull * d.N * sizeof(double) + 256));
+    IoPlan io(c);
+    double *dmu = io.slot(3ull * d.N), *dq = io.slot(3ull * d.N), *d0 = io.slot(d.P), *dT = io.slot(d.P);
+    double *dF = io.slot(d.N), *dphi = io.slot(d.N);
+    FOTO_TRY(h2d(c, dmu, mu, 3ull * d.N)); FOTO_TRY(h2d(c, dq, q, 3ull * d.N));
+    FOTO_TRY(h2d(c, d0, rho0, d.P)); FOTO_TRY(h2d(c, dT, rhoT, d.P));
+    launch_rhs(c->stream, d, dmu, dq, d0, dT, r, dF);
+    c->stats.launches++;
+    FOTO_TRY(run_cg(c, d, dF, dphi, (double *)c->ws, r, eps, backend));
+    FOTO_TRY(fetch_result(c));
+    if (cg_iters) *cg_iters = c->h_res->cg_iters;
+    if (cg_info) *cg_info = c->h_res->cg_info;
+    FOTO_TRY(d2h(c, phi, dphi, d.N));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    prof_resolve(c);
+    return FOTO_OK;
+}
+
+extern "C" int foto_flow_from_phi(const double *phi, int Nt, int Nx, int Ny, double *u, double *v, double *m)
+{
+    if (!phi || !u || !v || !m) { set_error("foto_flow_from_phi: NULL argument"); return FOTO_ERR_ARG; }
+    foto_ctx *c = nullptr;
+    FOTO_TRY(default_ctx(&c));
+    Dims d;
+    FOTO_TRY(make_dims(Nt, Nx, Ny, &d));
+    FOTO_TRY(ctx_bind(c));
+    FOTO_TRY(ensure(&c->io, &c->io_bytes, Carver::bytes(d.N) + 3 * Carver::bytes(d.P)));
+    IoPlan io(c);
+    double *dphi = io.slot(d.N), *du = io.slot(d.P), *dv = io.slot(d.P), *dm = io.slot(d.P);
+    FOTO_TRY(h2d(c, dphi, phi, d.N));
+    launch_flow(c->stream, d, dphi, du, dv, dm);
+    c->stats.launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    FOTO_TRY(d2h(c, u, du, d.P)); FOTO_TRY(d2h(c, v, dv, d.P)); FOTO_TRY(d2h(c, m, dm, d.P));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FOTO_OK;
+}
+
+// 1-D finite-difference builders of operators.py:5-110 as tridiagonal rows (lo, di, up).
+// The reference patches boundary rows after dividing by h, so those entries stay unscaled.
+extern "C" int foto_tri_coeffs(int kind, int n, double h, int bc, double *lo, double *di, double *up)
+{
+    if (bc != FOTO_BC_N && bc != FOTO_BC_D) { set_error("These boundary conditions are not implemented"); return FOTO_ERR_NOTIMPL; }
+    if (kind < 0 || kind > FOTO_1D_LAP) { set_error("unknown 1-D builder %d", kind); return FOTO_ERR_NOTIMPL; }
+    if (n < 2 || !lo || !di || !up) { set_error("1-D operator needs n >= 2"); return FOTO_ERR_ARG; }
+    const bool neumann = bc == FOTO_BC_N;
+    const double ih = 1.0 / h, hh = 0.5 / h, i2 = 1.0 / (h * h);
+    for (int i = 0; i < n; i++) {
+        const bool first = i == 0, last = i == n - 1;
+        double l = 0, d = 0, u = 0;
+        switch (kind) {
+        case FOTO_1D_FORWARD_WEIRD:  d = -ih; u = ih; if (last) { l = -1.0; d = 1.0; } break;
+        case FOTO_1D_BACKWARD_WEIRD: l = -ih; d = ih; if (first) { d = -1.0; u = 1.0; } break;
+        case FOTO_1D_CENTRAL_WEIRD:
+            l = -hh; u = hh;
+            if (neumann && first) { d = -1.0; u = 1.0; }
+            if (neumann && last) { d = 1.0; l = -1.0; }
+            break;
+        case FOTO_1D_CENTRAL: l = -hh; u = hh; if (neumann && (first || last)) { l = 0; u = 0; } break;
+        case FOTO_1D_FORWARD: d = -ih; u = ih; if (neumann && last) d = 0; break;
+        case FOTO_1D_BACKWARD: l = -ih; d = ih; if (neumann && first) d = 0; break;
+        case FOTO_1D_LAP:
+            l = i2; d = -2.0 * i2; u = i2;
+            if (neumann && (first || last)) d = -i2;
+            break;
+        }
+        if (first) l = 0;
+        if (last) u = 0;
+        lo[i] = l; di[i] = d; up[i] = u;
+    }
+    return FOTO_OK;
+}
+
+extern "C" int foto_op_apply(int op, int bc, int Nt, int Nx, int Ny, double dt, double dx, double dy, int transpose,
+                             const double *in, double *out)
+{
+    if (!in || !out) { set_error("foto_op_apply: NULL argument"); return FOTO_ERR_ARG; }
+    if (op < 0 || op > FOTO_OP_GRAD_FORWARD) { set_error("unknown operator %d", op); return FOTO_ERR_NOTIMPL; }
+    const bool three_d = op <= FOTO_OP_LAPLACIAN_ST;
+    if (!three_d) Nt = 1;
+    if (Nx < 2 || Ny < 2 || (three_d && Nt < 2)) { set_error("operator grid must be at least 2 per axis"); return FOTO_ERR_ARG; }
+    const int kind = (op == FOTO_OP_GRAD_ST || op == FOTO_OP_DIV_ST) ? FOTO_1D_CENTRAL_WEIRD
+                   : op == FOTO_OP_LAPLACIAN_ST ? FOTO_1D_LAP
+                   : op == FOTO_OP_GRAD_FORWARD ? FOTO_1D_FORWARD : FOTO_1D_CENTRAL;
+    const int lens[3] = {Nx, Ny, Nt};
+    const double hs[3] = {dx, dy, dt};
+    int mx = Nx > Ny ? Nx : Ny; if (Nt > mx) mx = Nt;
+    std::vector<double> hc(9 * (size_t)mx, 0.0);
+    const int naxes = three_d ? 3 : 2;
+    for (int ax = 0; ax < naxes; ax++)
+        FOTO_TRY(foto_tri_coeffs(kind, lens[ax], hs[ax], bc, &hc[(3 * ax) * mx], &hc[(3 * ax + 1) * mx], &hc[(3 * ax + 2) * mx]));
+    foto_ctx *c = nullptr;
+    FOTO_TRY(default_ctx(&c));
+    const unsigned long long P = (unsigned long long)Nx * Ny, N = P * Nt;
+    if (3ull * N >= (1ull << 32)) { set_error("grid too large"); return FOTO_ERR_ARG; }
+    const int ncomp = naxes;
+    const bool stack_out = (op == FOTO_OP_GRAD_ST || op == FOTO_OP_GRAD || op == FOTO_OP_GRAD_FORWARD);
+    const bool single = op == FOTO_OP_LAPLACIAN_ST;
+    const bool one_to_many = !single && (stack_out != (transpose != 0));
+    const size_t n_in = single ? N : (one_to_many ? N : ncomp * N), n_out = single ? N : (one_to_many ? ncomp * N : N);
+    FOTO_TRY(ctx_bind(c));
+    FOTO_TRY(ensure(&c->io, &c->io_bytes, Carver::bytes(n_in) + Carver::bytes(n_out) + Carver::bytes(hc.size())));
+    IoPlan io(c);
+    double *din = io.slot(n_in), *dout = io.slot(n_out), *dc = io.slot(hc.size());
+    FOTO_TRY(h2d(c, din, in, n_in));
+    FOTO_TRY(h2d(c, dc, hc.data(), hc.size()));
+    const unsigned int strides[3] = {1u, (unsigned int)Nx, (unsigned int)P};
+    // block order of the reference: [t, x, y] for space-time operators, [x, y] in 2-D
+    const int order3[3] = {2, 0, 1}, order2[2] = {0, 1};
+    const int *order = three_d ? order3 : order2;
+    for (int b = 0; b < naxes; b++) {
+        const int ax = order[b];
+        const double *lo = dc + (3 * ax) * mx, *di = dc + (3 * ax + 1) * mx, *up = dc + (3 * ax + 2) * mx;
+        const double *src = (single || one_to_many) ? din : din + (size_t)b * N;
+        double *dst = (single || !one_to_many) ? dout : dout + (size_t)b * N;
+        const int accumulate = (single || !one_to_many) && b > 0;
+        launch_axis_apply(c->stream, src, dst, lo, di, up, transpose, strides[ax], lens[ax], (unsigned int)N, accumulate);
+        c->stats.launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    FOTO_TRY(d2h(c, out, dout, n_out));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FOTO_OK;
+}
+
+static int gn_on_ctx(foto_ctx *c, const double *f1, const double *f2, int w, int h, double alpha, double lambda,
+                     double rtol, int max_it, double *u, double *v, double *m, int *iters, int *info)
+{
+    if (!f1 || !f2 || !u || !v || !m) { set_error("foto_gn_solve: NULL argument"); return FOTO_ERR_ARG; }
+    if (w < 2 || h < 2) { set_error("image must be at least 2x2"); return FOTO_ERR_ARG; }
+    const size_t P = (size_t)w * h;
+    FOTO_TRY(ctx_bind(c));
+    FOTO_TRY(ensure(&c->io, &c->io_bytes, 5 * Carver::bytes(P)));
+    IoPlan io(c);
+    double *d1 = io.slot(P), *d2 = io.slot(P), *du = io.slot(P), *dv = io.slot(P), *dm = io.slot(P);
+    FOTO_TRY(h2d(c, d1, f1, P)); FOTO_TRY(h2d(c, d2, f2, P));
+    FOTO_TRY(foto_gn_solve_dev(c, d1, d2, w, h, alpha, lambda, rtol, max_it, du, dv, dm, iters, info));
+    FOTO_TRY(d2h(c, u, du, P)); FOTO_TRY(d2h(c, v, dv, P)); FOTO_TRY(d2h(c, m, dm, P));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FOTO_OK;
+}
+
+extern "C" int foto_gn_solve(const double *f1, const double *f2, int w, int h, double alpha, double lambda,
+                             double rtol, int max_it, double *u, double *v, double *m, int *iters, int *info)
+{
+    foto_ctx *c = nullptr;
+    FOTO_TRY(default_ctx(&c));
+    return gn_on_ctx(c, f1, f2, w, h, alpha, lambda, rtol, max_it, u, v, m, iters, info);
+}
+
+extern "C" int foto_gn_system(const double *f1, const double *f2, int w, int h, double alpha, double lambda,
+                              const double *x, double *y, double *b)
+{
+    if (!f1 || !f2 || !x || !y || !b) { set_error("foto_gn_system: NULL argument"); return FOTO_ERR_ARG; }
+    if (w < 2 || h < 2) { set_error("image must be at least 2x2"); return FOTO_ERR_ARG; }
+    foto_ctx *c = nullptr;
+    FOTO_TRY(default_ctx(&c));
+    const size_t P = (size_t)w * h;
+    FOTO_TRY(ctx_bind(c));
+    FOTO_TRY(ensure(&c->io, &c->io_bytes, 4 * Carver::bytes(P) + 4 * Carver::bytes(3 * P)));
+    IoPlan io(c);
+    double *d1 = io.slot(P), *d2 = io.slot(P), *fx = io.slot(P), *fy = io.slot(P);
+    double *dinv = io.slot(3 * P), *db = io.slot(3 * P), *dx = io.slot(3 * P), *dy = io.slot(3 * P);
+    FOTO_TRY(h2d(c, d1, f1, P)); FOTO_TRY(h2d(c, d2, f2, P)); FOTO_TRY(h2d(c, dx, x, 3 * P));
+    launch_gn_coeffs(c->stream, w, h, d1, d2, alpha, lambda, fx, fy, dinv, db);
+    launch_gn_apply(c->stream, w, h, fx, fy, d2, alpha, lambda, dx, dy);
+    c->stats.launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    FOTO_TRY(d2h(c, y, dy, 3 * P)); FOTO_TRY(d2h(c, b, db, 3 * P));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FOTO_OK;
+}
+
+extern "C" int foto_warp_apply(const double *f1, const double *u, const double *v, int w, int h, const double *m,
+                               double *out)
+{
+    if (!f1 || !u || !v || !out) { set_error("foto_warp_apply: NULL argument"); return FOTO_ERR_ARG; }
+    if (w < 1 || h < 1) { set_error("empty image"); return FOTO_ERR_ARG; }
+    foto_ctx *c = nullptr;
+    FOTO_TRY(default_ctx(&c));
+    const size_t P = (size_t)w * h;
+    FOTO_TRY(ctx_bind(c));
+    FOTO_TRY(ensure(&c->io, &c->io_bytes, 6 * Carver::bytes(P)));
+    IoPlan io(c);
+    double *df = io.slot(P), *du = io.slot(P), *dv = io.slot(P), *dm = io.slot(P), *dg = io.slot(P), *dout = io.slot(P);
+    FOTO_TRY(h2d(c, df, f1, P)); FOTO_TRY(h2d(c, du, u, P)); FOTO_TRY(h2d(c, dv, v, P));
+    if (m) FOTO_TRY(h2d(c, dm, m, P));
+    launch_warp(c->stream, w, h, df, du, dv, m ? dm : nullptr, dg, dout);
+    c->stats.launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    FOTO_TRY(d2h(c, out, dout, P));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FOTO_OK;
+}
+
+// ------------------------------------------------------------------------------- batch driver
+// Pairs are independent: one host thread per device pulls pair indices
+// from an atomic counter (dynamic load balance: iteration counts are data dependent), runs the
+// whole solve on its device and writes straight into the caller's output rows.  No collective.
+template <class Fn>
+static int run_batch(int n_items, const int *device_ids, int n_dev, Fn per_item)
+{
+    if (n_items < 0 || n_dev < 1) { set_error("batch: need n_pairs >= 0 and n_dev >= 1"); return FOTO_ERR_ARG; }
+    int have = foto_device_count();
+    if (have <= 0) { if (have == 0) set_error("no CUDA device: libfoto_b200 has no CPU fallback"); return FOTO_ERR_NODEV; }
+    std::atomic<int> next(0), first_rc(FOTO_OK);
+    std::mutex err_mutex;
+    std::string err_msg;
+    std::vector<std::thread> threads;
+    for (int t = 0; t < n_dev; t++) {
+        const int dev = device_ids ? device_ids[t] : t;
+        threads.emplace_back([&, dev]() {
+            foto_ctx *c = nullptr;
+            int rc = foto_ctx_create(dev, &c);
+            while (rc == FOTO_OK) {
+                const int i = next.fetch_add(1);
+                if (i >= n_items || first_rc.load() != FOTO_OK) break;
+                rc = per_item(c, i);
+            }
+            if (rc != FOTO_OK) {
+                std::lock_guard<std::mutex> lk(err_mutex);
+                if (first_rc.load() == FOTO_OK) { first_rc.store(rc); err_msg = foto_last_error(); }
+            }
+            foto_ctx_destroy(c);
+        });
+    }
+    for (auto &th : threads) th.join();
+    if (first_rc.load() != FOTO_OK) set_error("%s", err_msg.c_str());
+    return first_rc.load();
+}
+
+extern "C" int foto_solve_batch(int n_pairs, const double *rho0s, const double *rhoTs, int Nt, int Nx, int Ny,
+                                double r, double tol, double eps, int max_it, int backend, const int *device_ids,
+                                int n_dev, double *us, double *vs, double *ms, int *n_outer)
+{
+    if (!rho0s || !rhoTs || !us || !vs || !ms) { set_error("foto_solve_batch: NULL argument"); return FOTO_ERR_ARG; }
+    const size_t P = (size_t)Nx * Ny;
+    return run_batch(n_pairs, device_ids, n_dev, [&](foto_ctx *c, int i) {
+        int outer = 0;
+        int rc = solve_on_ctx(c, rho0s + i * P, rhoTs + i * P, Nt, Nx, Ny, r, tol, eps, max_it, backend, us + i * P,
+                              vs + i * P, ms + i * P, nullptr, &outer, nullptr, nullptr);
+        if (n_outer) n_outer[i] = outer;
+        return rc;
+    });
+}
+
+extern "C" int foto_gn_solve_batch(int n_pairs, const double *f1s, const double *f2s, int w, int h, double alpha,
+                                   double lambda, double rtol, int max_it, const int *device_ids, int n_dev,
+                                   double *us, double *vs, double *ms, int *iters)
+{
+    if (!f1s || !f2s || !us || !vs || !ms) { set_error("foto_gn_solve_batch: NULL argument"); return FOTO_ERR_ARG; }
+    const size_t P = (size_t)w * h;
+    return run_batch(n_pairs, device_ids, n_dev, [&](foto_ctx *c, int i) {
+        int it = 0, info = 0;
+        int rc = gn_on_ctx(c, f1s + i * P, f2s + i * P, w, h, alpha, lambda, rtol, max_it, us + i * P, vs + i * P,
+                           ms + i * P, &it, &info);
+        if (iters) iters[i] = it;
+        return rc;
+    });
+}

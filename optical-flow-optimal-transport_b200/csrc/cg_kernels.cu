@@ -1,0 +1,145 @@
+// cg_kernels.cu -- K2a: the Poisson solve of stepA as ONE persistent cooperative kernel.
+//
+// Restates scipy.sparse.linalg.cg (x0 = 0, no preconditioner) as called at
+// benamou_brenier.py:85 on A = -r L_st + r eps I (benamou_brenier.py:201-203):
+//     atol = rtol ||b||;  r = b;  loop k < maxiter:
+//         if ||r|| < atol: return (x, 0)
+//         rho = r.r;  p = r + (rho/rho_prev) p   (p = r on the first pass)
+//         q = A p;  alpha = rho / (p.q);  x += alpha p;  r -= alpha q
+//     return (x, maxiter)
+// The truncation error of this recurrence at rtol 1e-6 is part of the reference's answer
+// (SURVEY.md parity trap #1), so the recurrence is reproduced operation for operation; A p is
+// accumulated in csr_matvec's column order (t-1, y-1, x-1, diag, x+1, y+1, t+1).
+//
+// Streaming variant (this file, cg_stream_kernel): vectors live in global memory (L2-resident up
+// to ~10 M cells, HBM beyond).  Two grid-wide barriers per iteration, each fused with the
+// all-reduce of the dot product it guards:
+//   phase A: p_new = r + beta p_old at the 7 stencil points (p is double-buffered so that
+//            neighbours can be recomputed instead of synchronised), q = A p_new, partial p.q
+//   phase B: x += alpha p_new, r -= alpha q, partial r.r
+// Algorithmic traffic: 11 words per cell per iteration; this
+// kernel moves 10 (r, p_old read; p_new, q written; x, p_new, r, q read; x, r written).
+#include "foto_kernels.cuh"
+
+namespace foto {
+
+namespace {
+
+struct Coef {            // matrix entries of A, exactly as the reference assembles them
+    double off;          // -r * 1.0
+    double reps;         // r * eps * 1.0
+    double r;
+};
+
+// diagonal entry of A for a cell with the given boundary flags: -r * L_ii + r*eps
+__device__ __forceinline__ double diag_entry(const Coef &c, bool bt, bool by, bool bx)
+{
+    const double Lii = (bt ? -1.0 : -2.0) + ((bx ? -1.0 : -2.0) + (by ? -1.0 : -2.0));
+    return -c.r * Lii + c.reps;
+}
+
+__global__ void __launch_bounds__(512, 2) cg_stream_kernel(CgArgs a)
+{
+    __shared__ double red[128];
+    const unsigned int P = (unsigned int)a.Nx * (unsigned int)a.Ny;
+    const unsigned int N = P * (unsigned int)a.Nt;
+    const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int nth = gridDim.x * blockDim.x;
+    const int Nx = a.Nx, Ny = a.Ny, Nt = a.Nt;
+    Coef c;
+    c.r = a.rcoef; c.off = -a.rcoef * 1.0; c.reps = a.rcoef * a.eps * 1.0;
+    unsigned int gen = 0;
+
+    // r = b, x = 0, p_old = 0, ||b||^2
+    double acc[1] = {0.0};
+    for (unsigned int k = tid; k < N; k += nth) {
+        const double bk = a.b[k];
+        a.r[k] = bk; a.x[k] = 0.0; a.p0[k] = 0.0;
+        acc[0] += bk * bk;
+    }
+    grid_allreduce<1>(a.sync, gen, acc, red);
+    const double bb = acc[0];
+    if (*a.sync.error) return;
+    if (bb == 0.0) {                                  // scipy: "if bnrm2 == 0: return b, 0"
+        if (tid == 0) { a.out[0] = 0; a.out[1] = 0; }
+        return;                                       // x already holds zeros (= b)
+    }
+    const double atol = a.rtol * sqrt(bb);
+    double rr = bb, rr_prev = 0.0;
+    double *pold = a.p0, *pnew = a.p1;
+    int it = 0, info = a.maxiter;
+    for (; it < a.maxiter; it++) {
+        if (sqrt(rr) < atol) { info = 0; break; }
+        const double beta = it > 0 ? rr / rr_prev : 0.0;
+        // ---- phase A
+        acc[0] = 0.0;
+        for (unsigned int k = tid; k < N; k += nth) {
+            const unsigned int row = k / (unsigned int)Nx;
+            const int x = (int)(k - row * (unsigned int)Nx);
+            const unsigned int nn = row / (unsigned int)Ny;
+            const int y = (int)(row - nn * (unsigned int)Ny);
+            const int n = (int)nn;
+            const double pc = pold[k] * beta + a.r[k];
+            double s = 0.0;
+            if (n > 0) s += c.off * (pold[k - P] * beta + a.r[k - P]);
+            if (y > 0) s += c.off * (pold[k - Nx] * beta + a.r[k - Nx]);
+            if (x > 0) s += c.off * (pold[k - 1] * beta + a.r[k - 1]);
+            s += diag_entry(c, n == 0 || n == Nt - 1, y == 0 || y == Ny - 1, x == 0 || x == Nx - 1) * pc;
+            if (x < Nx - 1) s += c.off * (pold[k + 1] * beta + a.r[k + 1]);
+            if (y < Ny - 1) s += c.off * (pold[k + Nx] * beta + a.r[k + Nx]);
+            if (n < Nt - 1) s += c.off * (pold[k + P] * beta + a.r[k + P]);
+            pnew[k] = pc;
+            a.q[k] = s;
+            acc[0] += pc * s;
+        }
+        grid_allreduce<1>(a.sync, gen, acc, red);
+        if (*a.sync.error) return;
+        const double alpha = rr / acc[0];
+        // ---- phase B
+        acc[0] = 0.0;
+        for (unsigned int k = tid; k < N; k += nth) {
+            const double xk = a.x[k] + alpha * pnew[k];
+            const double rk = a.r[k] - alpha * a.q[k];
+            a.x[k] = xk; a.r[k] = rk;
+            acc[0] += rk * rk;
+        }
+        grid_allreduce<1>(a.sync, gen, acc, red);
+        if (*a.sync.error) return;
+        rr_prev = rr; rr = acc[0];
+        double *t = pold; pold = pnew; pnew = t;
+    }
+    if (tid == 0) { a.out[0] = it; a.out[1] = info; }
+}
+
+}  // namespace
+
+int cg_stream_config(int device, int *grid, int *block)
+{
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    int per_sm = 0;
+    *block = 512;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_stream_kernel, *block, 0));
+    if (per_sm < 1) { set_error("cg_stream_kernel does not fit on an SM"); return FOTO_ERR_CUDA; }
+    if (per_sm > 2) per_sm = 2;
+    *grid = per_sm * prop.multiProcessorCount;
+    if (*grid > kMaxBlocks) *grid = kMaxBlocks;
+    return FOTO_OK;
+}
+
+int launch_cg_stream(cudaStream_t st, const CgArgs &a, int grid, int block)
+{
+    CUDA_TRY(cudaMemsetAsync(a.sync.counter, 0, sizeof(unsigned int), st));
+    void *args[] = {(void *)&a};
+    CUDA_TRY(cudaLaunchCooperativeKernel((void *)cg_stream_kernel, dim3(grid), dim3(block), args, 0, st));
+    return FOTO_OK;
+}
+
+bool cg_onchip_fits(int, int, int, int) { return false; }
+int launch_cg_onchip(cudaStream_t, const CgArgs &, int)
+{
+    set_error("on-chip CG variant not built");
+    return FOTO_ERR_ARG;
+}
+
+}  // namespace foto

@@ -1,0 +1,348 @@
+// foto_kernels.cu -- FOTO pointwise / stencil kernels (K1, K3, K4, K7, operator apply).
+//
+// All kernels are fp64, structure-of-arrays, flat index k = n*P + y*Nx + x (x fastest), so
+// consecutive threads touch consecutive doubles (fully coalesced 256 B per warp request).
+// The file is compiled with -fmad=false: the reference evaluates every product and sum
+// separately (numpy / scipy sparse mat-vec), and keeping that rounding makes K1 and K4
+// bit-identical to it and keeps the truncated-CG iterates within 1e-11 of the reference.
+#include "foto_kernels.cuh"
+
+namespace foto {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void decode(unsigned int k, const Dims &d, int &n, int &y, int &x)
+{
+    unsigned int row = k / (unsigned int)d.Nx;
+    x = (int)(k - row * (unsigned int)d.Nx);
+    unsigned int nn = row / (unsigned int)d.Ny;
+    y = (int)(row - nn * (unsigned int)d.Ny);
+    n = (int)nn;
+}
+
+// "weird" central difference with one-sided Neumann rows (operators.py:33-48), unit spacing
+__device__ __forceinline__ double dw(const double *__restrict__ f, unsigned int k, unsigned int st, int i, int n)
+{
+    if (i == 0) return f[k + st] - f[k];
+    if (i == n - 1) return f[k] - f[k - st];
+    return 0.5 * f[k + st] - 0.5 * f[k - st];
+}
+
+// --------------------------------------------------------------------------- init
+__global__ void __launch_bounds__(kThreads) k_init_state(Dims d, const double *__restrict__ rho0,
+                                                          const double *__restrict__ rhoT,
+                                                          double *__restrict__ mu, double *__restrict__ q)
+{
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < d.N; k += stride) {
+        unsigned int n = k / d.P, i = k - n * d.P;
+        // (1 - n/(Nt-1))*rho0 + (n/(Nt-1))*rhoT     (benamou_brenier.py:193-194)
+        double w2 = (double)n / (double)(d.Nt - 1);
+        double w1 = 1.0 - w2;
+        mu[k] = w1 * rho0[i] + w2 * rhoT[i];
+        mu[d.N + k] = 0.0;
+        mu[2u * d.N + k] = 0.0;
+        q[k] = 0.0;
+        q[d.N + k] = 0.0;
+        q[2u * d.N + k] = 0.0;
+    }
+}
+
+// --------------------------------------------------------------------------- K1
+// w = mu - r q evaluated at the stencil points; running sum in scipy coo_matvec order:
+// t-block (n-1, n+1), x-block (x-1, x+1), y-block (y-1, y+1); then the rho0/rhoT terms.
+__device__ __forceinline__ double wv(const double *__restrict__ mu, const double *__restrict__ q, double r, unsigned int k)
+{
+    return mu[k] - r * q[k];
+}
+
+__device__ __forceinline__ double dw_acc(double s, const double *__restrict__ mu, const double *__restrict__ q,
+                                         double r, unsigned int k, unsigned int st, int i, int n)
+{
+    if (i == 0) { s += -1.0 * wv(mu, q, r, k); s += 1.0 * wv(mu, q, r, k + st); }
+    else if (i == n - 1) { s += -1.0 * wv(mu, q, r, k - st); s += 1.0 * wv(mu, q, r, k); }
+    else { s += -0.5 * wv(mu, q, r, k - st); s += 0.5 * wv(mu, q, r, k + st); }
+    return s;
+}
+
+__global__ void __launch_bounds__(kThreads) k_rhs(Dims d, const double *__restrict__ mu, const double *__restrict__ q,
+                                                   const double *__restrict__ rho0, const double *__restrict__ rhoT,
+                                                   double r, double *__restrict__ F)
+{
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < d.N; k += stride) {
+        int n, y, x;
+        decode(k, d, n, y, x);
+        double s = 0.0;
+        s = dw_acc(s, mu, q, r, k, d.P, n, d.Nt);
+        s = dw_acc(s, mu + d.N, q + d.N, r, k, 1u, x, d.Nx);
+        s = dw_acc(s, mu + 2u * d.N, q + 2u * d.N, r, k, (unsigned int)d.Nx, y, d.Ny);
+        unsigned int i = k - (unsigned int)n * d.P;
+        if (n == 0) s -= (rho0[i] - mu[k] + r * q[k]);
+        if (n == d.Nt - 1) s += (rhoT[i] - mu[k] + r * q[k]);
+        F[k] = s;
+    }
+}
+
+// --------------------------------------------------------------------------- stepB
+// Projection of (alpha, beta1, beta2) onto K = {alpha + |beta|^2/2 <= 0}
+// (benamou_brenier.py:123-147), with the algebraic forms SURVEY.md section 7 verified:
+//   4/3 a^3 + 4 a^2 + 4 a + 4/3 = 4/3 (a+1)^3,  cos(atan2(b2,b1)) = b1/rho, sin = b2/rho,
+//   pow(s, 1/3) = cbrt(s),  zh = c - (a+1)/(3c).
+__device__ __forceinline__ void project_K(double a, double b1, double b2, double &qa, double &qb1, double &qb2)
+{
+    const double rho2 = b1 * b1 + b2 * b2;
+    if (2.0 * a + rho2 <= 0.0) { qa = a; qb1 = b1; qb2 = b2; return; }
+    const double rho = sqrt(rho2);
+    const double a1 = a + 1.0;
+    const double cube = a1 * a1 * a1;
+    double aH, rhoH;
+    if (-32.0 * cube - 108.0 * rho2 < 0.0) {                 // single real root
+        const double rad = (4.0 / 3.0) * cube + 4.5 * rho2;
+        const double s = 0.35355339059327379 * rho + (1.0 / 6.0) * sqrt(rad);   // sqrt(2)/4
+        const double c = cbrt(s);
+        const double zh = c - a1 / (3.0 * c);
+        aH = -(zh * zh);
+        rhoH = 1.4142135623730951 * zh;
+    } else {                                                  // three real roots
+        const double t = -a1;
+        const double arg = 1.8371173070873836 * rho / (t * sqrt(t));            // (3/2)^(3/2)
+        const double zh = 1.6329931618554521 * sqrt(t) * cos(acos(arg) / 3.0);  // 2 sqrt(2/3)
+        aH = -0.5 * (zh * zh);
+        rhoH = zh;
+    }
+    double ct = 1.0, st = 0.0;                                // atan2(0, 0) = 0
+    if (rho > 0.0) { ct = b1 / rho; st = b2 / rho; }
+    qa = aH; qb1 = rhoH * ct; qb2 = rhoH * st;
+}
+
+__global__ void __launch_bounds__(kThreads) k_stepB(unsigned int N, const double *__restrict__ p, double *__restrict__ q)
+{
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += stride) {
+        double qa, qb1, qb2;
+        project_K(p[k], p[N + k], p[2u * N + k], qa, qb1, qb2);
+        q[k] = qa; q[N + k] = qb1; q[2u * N + k] = qb2;
+    }
+}
+
+// --------------------------------------------------------------------------- K3
+// gradPhi = grad_st phi (registers only); p = gradPhi + mu/r; q = stepB(p);
+// mu += r (gradPhi - q); mu_rho = max(mu_rho, 0); criterion partial sums with the updated mu.
+__global__ void __launch_bounds__(kThreads) k_prox_dual(Dims d, const double *__restrict__ phi, double *__restrict__ mu,
+                                                         double *__restrict__ q, double r, double inv_r,
+                                                         double *__restrict__ partials)
+{
+    __shared__ double red[64];
+    double acc[2] = {0.0, 0.0};
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < d.N; k += stride) {
+        int n, y, x;
+        decode(k, d, n, y, x);
+        const double gt = dw(phi, k, d.P, n, d.Nt);
+        const double gx = dw(phi, k, 1u, x, d.Nx);
+        const double gy = dw(phi, k, (unsigned int)d.Nx, y, d.Ny);
+        const double m0 = mu[k], m1 = mu[d.N + k], m2 = mu[2u * d.N + k];
+        double qa, qb1, qb2;
+        project_K(gt + inv_r * m0, gx + inv_r * m1, gy + inv_r * m2, qa, qb1, qb2);
+        q[k] = qa; q[d.N + k] = qb1; q[2u * d.N + k] = qb2;
+        double rho = m0 + r * (gt - qa);
+        rho = fmax(rho, 0.0);
+        mu[k] = rho;
+        mu[d.N + k] = m1 + r * (gx - qb1);
+        mu[2u * d.N + k] = m2 + r * (gy - qb2);
+        const double g2 = gx * gx + gy * gy;
+        const double res = gt + 0.5 * g2;
+        acc[0] += rho * fabs(res);
+        acc[1] += rho * g2;
+    }
+    block_sum<2>(acc, red);
+    if (threadIdx.x == 0) { partials[2 * blockIdx.x] = acc[0]; partials[2 * blockIdx.x + 1] = acc[1]; }
+}
+
+__global__ void __launch_bounds__(kThreads) k_crit_final(const double *__restrict__ partials, int blocks, double *__restrict__ out2)
+{
+    __shared__ double red[64];
+    double acc[2] = {0.0, 0.0};
+    for (int b = threadIdx.x; b < blocks; b += blockDim.x) { acc[0] += partials[2 * b]; acc[1] += partials[2 * b + 1]; }
+    block_sum<2>(acc, red);
+    if (threadIdx.x == 0) { out2[0] = acc[0]; out2[1] = acc[1]; }
+}
+
+// --------------------------------------------------------------------------- K4
+// Velocity taps un = Dc_x phi_n, vn = Dc_y phi_n (grad_1d_central 'N': zero on the first and
+// last column/row, operators.py:61-63) are recomputed from phi at each bilinear tap; phi of one
+// time slice is L2-resident, so the 16 gathers per step cost no HBM traffic.
+__device__ __forceinline__ double tap_u(const double *__restrict__ ph, unsigned int i, int x, int Nx)
+{
+    return (x == 0 || x == Nx - 1) ? 0.0 : (0.5 * ph[i + 1] - 0.5 * ph[i - 1]);
+}
+__device__ __forceinline__ double tap_v(const double *__restrict__ ph, unsigned int i, int y, int Ny, int Nx)
+{
+    return (y == 0 || y == Ny - 1) ? 0.0 : (0.5 * ph[i + Nx] - 0.5 * ph[i - Nx]);
+}
+
+__global__ void __launch_bounds__(kThreads) k_trajectories(Dims d, const double *__restrict__ phi,
+                                                            double *__restrict__ u, double *__restrict__ v)
+{
+    const unsigned int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 >= d.P) return;
+    const int ys = (int)(i0 / (unsigned int)d.Nx), xs = (int)(i0 - (unsigned int)ys * d.Nx);
+    double xe = (double)xs, ye = (double)ys;
+    for (int n = 0; n < d.Nt - 1; n++) {
+        // int() truncation toward zero, then clamp to [0, N-2] (utils.py:63-68); the clamp is
+        // done in double so that huge / negative excursions behave like Python's unbounded int
+        double tx = trunc(xe), ty = trunc(ye);
+        tx = fmin(tx, (double)(d.Nx - 2)); tx = fmax(tx, 0.0);
+        ty = fmin(ty, (double)(d.Ny - 2)); ty = fmax(ty, 0.0);
+        const int ix = (int)tx, iy = (int)ty;
+        const double dX = xe - (double)ix, dY = ye - (double)iy;
+        const double w1 = (1.0 - dY) * (1.0 - dX), w2 = dX * (1.0 - dY), w3 = dY * dX, w4 = (1.0 - dX) * dY;
+        const double *ph = phi + (size_t)n * d.P;
+        const unsigned int i00 = (unsigned int)iy * d.Nx + ix;
+        const double u00 = tap_u(ph, i00, ix, d.Nx), u01 = tap_u(ph, i00 + 1, ix + 1, d.Nx);
+        const double u11 = tap_u(ph, i00 + d.Nx + 1, ix + 1, d.Nx), u10 = tap_u(ph, i00 + d.Nx, ix, d.Nx);
+        const double v00 = tap_v(ph, i00, iy, d.Ny, d.Nx), v01 = tap_v(ph, i00 + 1, iy, d.Ny, d.Nx);
+        const double v11 = tap_v(ph, i00 + d.Nx + 1, iy + 1, d.Ny, d.Nx), v10 = tap_v(ph, i00 + d.Nx, iy + 1, d.Ny, d.Nx);
+        xe += (w1 * u00 + w2 * u01 + w3 * u11 + w4 * u10);
+        ye += (w1 * v00 + w2 * v01 + w3 * v11 + w4 * v10);
+    }
+    u[i0] = xe - (double)xs;
+    v[i0] = ye - (double)ys;
+}
+
+// m = -div(u, v) with grad_1d_central 'D' (zero extension), summed in coo_matvec order
+__global__ void __launch_bounds__(kThreads) k_luminosity(Dims d, const double *__restrict__ u, const double *__restrict__ v,
+                                                          double *__restrict__ m)
+{
+    const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= d.P) return;
+    const int y = (int)(k / (unsigned int)d.Nx), x = (int)(k - (unsigned int)y * d.Nx);
+    double s = 0.0;
+    if (x > 0) s += -0.5 * u[k - 1];
+    if (x + 1 < d.Nx) s += 0.5 * u[k + 1];
+    if (y > 0) s += -0.5 * v[k - d.Nx];
+    if (y + 1 < d.Ny) s += 0.5 * v[k + d.Nx];
+    m[k] = -s;
+}
+
+// --------------------------------------------------------------------------- K7
+__global__ void __launch_bounds__(kThreads) k_scale_lum(unsigned int P, const double *__restrict__ f1,
+                                                         const double *__restrict__ m, double *__restrict__ g)
+{
+    const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < P) g[k] = m ? (1.0 + m[k]) * f1[k] : f1[k];
+}
+
+// Backward bilinear warp with the reference's quirks (utils.py:205-247): fractions are taken
+// BEFORE clamping, truncation is toward zero, the lower row index is int(tildI + 1), and the
+// four taps are accumulated left to right.
+__global__ void __launch_bounds__(kThreads) k_warp(int w, int h, const double *__restrict__ g, const double *__restrict__ u,
+                                                    const double *__restrict__ v, double *__restrict__ out)
+{
+    const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (unsigned int)w * (unsigned int)h) return;
+    const int i = (int)(k / (unsigned int)w), j = (int)(k - (unsigned int)i * w);
+    double tI = (double)i - v[k], tJ = (double)j - u[k];
+    const double dI = tI - trunc(tI), dJ = tJ - trunc(tJ);
+    const double w1 = (1.0 - dI) * (1.0 - dJ), w2 = dJ * (1.0 - dI), w3 = dI * dJ, w4 = (1.0 - dJ) * dI;
+    if (tI >= (double)h) tI = (double)(h - 1);
+    if (tJ >= (double)w) tJ = (double)(w - 1);
+    if (tI < 0.0) tI = 0.0;
+    if (tJ < 0.0) tJ = 0.0;
+    const int I = (int)tI, J = (int)tJ, I1 = (int)(tI + 1.0);
+    const bool right = (J == w - 1), bottom = (I == h - 1);
+    const size_t r0 = (size_t)I * w, r1 = (size_t)(bottom ? I : I1) * w;
+    const int J1 = right ? J : J + 1;
+    double x = w1 * g[r0 + J];
+    x = x + w2 * g[r0 + J1];
+    x = x + w3 * g[r1 + J1];
+    x = x + w4 * g[r1 + J];
+    out[k] = x;
+}
+
+// --------------------------------------------------------------------------- operators
+__global__ void __launch_bounds__(kThreads) k_axis_apply(const double *__restrict__ in, double *__restrict__ out,
+                                                          const double *__restrict__ lo, const double *__restrict__ di,
+                                                          const double *__restrict__ up, int transpose,
+                                                          unsigned int stride, int len, unsigned int total, int accumulate)
+{
+    const unsigned int gs = gridDim.x * blockDim.x;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gs) {
+        const int c = (int)((k / stride) % (unsigned int)len);
+        double s = 0.0;
+        if (!transpose) {
+            if (c > 0) s += lo[c] * in[k - stride];
+            s += di[c] * in[k];
+            if (c + 1 < len) s += up[c] * in[k + stride];
+        } else {
+            if (c > 0) s += up[c - 1] * in[k - stride];
+            s += di[c] * in[k];
+            if (c + 1 < len) s += lo[c + 1] * in[k + stride];
+        }
+        out[k] = accumulate ? out[k] + s : s;
+    }
+}
+
+inline int blocks_for(unsigned int n, int cap = 148 * 16)
+{
+    unsigned int b = (n + kThreads - 1) / kThreads;
+    return (int)(b < (unsigned int)cap ? (b ? b : 1) : (unsigned int)cap);
+}
+
+}  // namespace
+
+void launch_init_state(cudaStream_t st, Dims d, const double *rho0, const double *rhoT, double *mu, double *q)
+{
+    k_init_state<<<blocks_for(d.N), kThreads, 0, st>>>(d, rho0, rhoT, mu, q);
+}
+
+void launch_rhs(cudaStream_t st, Dims d, const double *mu, const double *q, const double *rho0, const double *rhoT,
+                double r, double *F)
+{
+    k_rhs<<<blocks_for(d.N), kThreads, 0, st>>>(d, mu, q, rho0, rhoT, r, F);
+}
+
+int launch_prox_dual(cudaStream_t st, Dims d, const double *phi, double *mu, double *q, double r, double *partials,
+                     int max_blocks)
+{
+    int blocks = blocks_for(d.N, max_blocks);
+    k_prox_dual<<<blocks, kThreads, 0, st>>>(d, phi, mu, q, r, 1.0 / r, partials);
+    return blocks;
+}
+
+void launch_crit_final(cudaStream_t st, const double *partials, int blocks, double *out2)
+{
+    k_crit_final<<<1, kThreads, 0, st>>>(partials, blocks, out2);
+}
+
+void launch_stepB(cudaStream_t st, unsigned int N, const double *p, double *q)
+{
+    k_stepB<<<blocks_for(N), kThreads, 0, st>>>(N, p, q);
+}
+
+void launch_flow(cudaStream_t st, Dims d, const double *phi, double *u, double *v, double *m)
+{
+    const int blocks = (int)((d.P + kThreads - 1) / kThreads);
+    k_trajectories<<<blocks, kThreads, 0, st>>>(d, phi, u, v);
+    k_luminosity<<<blocks, kThreads, 0, st>>>(d, u, v, m);
+}
+
+void launch_warp(cudaStream_t st, int w, int h, const double *f1, const double *u, const double *v,
+                 const double *m_or_null, double *g, double *out)
+{
+    const unsigned int P = (unsigned int)w * (unsigned int)h;
+    const int blocks = (int)((P + kThreads - 1) / kThreads);
+    k_scale_lum<<<blocks, kThreads, 0, st>>>(P, f1, m_or_null, g);
+    k_warp<<<blocks, kThreads, 0, st>>>(w, h, g, u, v, out);
+}
+
+void launch_axis_apply(cudaStream_t st, const double *in, double *out, const double *lo, const double *di,
+                       const double *up, int transpose, unsigned int stride, int len, unsigned int total, int accumulate)
+{
+    k_axis_apply<<<blocks_for(total), kThreads, 0, st>>>(in, out, lo, di, up, transpose, stride, len, total, accumulate);
+}
+
+}  // namespace foto

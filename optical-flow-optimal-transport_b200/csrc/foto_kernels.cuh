@@ -1,0 +1,75 @@
+// foto_kernels.cuh -- launch wrappers of the sm_100a kernels (definitions in *.cu).
+#pragma once
+#include "common.cuh"
+
+namespace foto {
+
+struct Dims {
+    int Nt, Ny, Nx;
+    unsigned int P;     // Nx*Ny
+    unsigned int N;     // Nt*P   (grids up to 2^31-1 cells)
+};
+
+// ---- FOTO pointwise / stencil kernels (foto_kernels.cu) --------------------------------
+// mu <- [linear-in-time density | 0 | 0],  q <- 0          (benamou_brenier.py:191-194)
+void launch_init_state(cudaStream_t st, Dims d, const double *rho0, const double *rhoT, double *mu, double *q);
+// K1: F = div_st(mu - r q) + time-boundary terms            (benamou_brenier.py:64-82)
+void launch_rhs(cudaStream_t st, Dims d, const double *mu, const double *q, const double *rho0,
+                const double *rhoT, double r, double *F);
+// K3: grad_st phi, stepB, stepC, clamp, criterion partial sums (benamou_brenier.py:213-251)
+// partials: 2*blocks doubles; returns the number of blocks used.
+int launch_prox_dual(cudaStream_t st, Dims d, const double *phi, double *mu, double *q, double r,
+                     double *partials, int max_blocks);
+void launch_crit_final(cudaStream_t st, const double *partials, int blocks, double *out2);
+// stepB alone (benamou_brenier.py:93-149)
+void launch_stepB(cudaStream_t st, unsigned int N, const double *p, double *q);
+// K4: trajectories + luminosity (utils.py:44-99,148-183)
+void launch_flow(cudaStream_t st, Dims d, const double *phi, double *u, double *v, double *m);
+// K7: utils.apply_opticalflow (utils.py:186-248); g = scratch P doubles
+void launch_warp(cudaStream_t st, int w, int h, const double *f1, const double *u, const double *v,
+                 const double *m_or_null, double *g, double *out);
+// generic tridiagonal-along-one-axis apply used by foto_op_apply
+void launch_axis_apply(cudaStream_t st, const double *in, double *out, const double *lo, const double *di,
+                       const double *up, int transpose, unsigned int stride, int len, unsigned int total,
+                       int accumulate);
+
+// ---- persistent CG for stepA (cg_kernels.cu) -------------------------------------------
+struct CgArgs {
+    const double *b;        // right-hand side F (N)
+    double *x;              // solution phi (N)
+    double *r, *p0, *p1, *q;// work vectors (N each)
+    int Nt, Ny, Nx;
+    double rcoef;           // r
+    double eps;             // reg_epsilon
+    double rtol;
+    int maxiter;
+    SyncState sync;
+    int *out;               // [0] iterations, [1] info (0 converged / maxiter)
+};
+// Returns FOTO_OK or an error code.  grid/block are chosen by cg_stream_config().
+int cg_stream_config(int device, int *grid, int *block);
+int launch_cg_stream(cudaStream_t st, const CgArgs &a, int grid, int block);
+
+// on-chip resident variant (state in shared memory/registers, one tile per SM)
+bool cg_onchip_fits(int device, int Nt, int Ny, int Nx);
+int launch_cg_onchip(cudaStream_t st, const CgArgs &a, int device);
+
+// ---- Gennert-Negahdaripour (gn_kernels.cu) ---------------------------------------------
+// K5: fx, fy (central, zero on the border), ft, Jacobi inverse diagonal, right-hand side
+void launch_gn_coeffs(cudaStream_t st, int w, int h, const double *f1, const double *f2, double alpha,
+                      double lam, double *fx, double *fy, double *dinv, double *b);
+void launch_gn_apply(cudaStream_t st, int w, int h, const double *fx, const double *fy, const double *f2,
+                     double alpha, double lam, const double *x, double *y);
+struct GnArgs {
+    const double *fx, *fy, *f2, *dinv, *b;   // P, P, P, 3P, 3P
+    double *x, *r, *z, *p0, *p1, *q;         // 3P each
+    int w, h;
+    double alpha, lam, rtol;
+    int maxiter;
+    SyncState sync;
+    int *out;                                // [0] iterations, [1] info
+};
+int gn_pcg_config(int device, int *grid, int *block);
+int launch_gn_pcg(cudaStream_t st, const GnArgs &a, int grid, int block);
+
+}  // namespace foto

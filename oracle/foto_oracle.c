@@ -158,6 +158,15 @@ static inline double dw(const double *f, size_t k, size_t st, int i, int n)   /*
     return 0.5 * f[k + st] - 0.5 * f[k - st];
 }
 
+/* running-sum form of dw(): s += row entries in column order */
+static inline double dw_acc(double s, const double *f, size_t k, size_t st, int i, int n)
+{
+    if (i == 0) { s += -1.0 * f[k]; s += 1.0 * f[k + st]; }
+    else if (i == n - 1) { s += -1.0 * f[k - st]; s += 1.0 * f[k]; }
+    else { s += -0.5 * f[k - st]; s += 0.5 * f[k + st]; }
+    return s;
+}
+
 static inline double lap1(const double *f, size_t k, size_t st, int i, int n)  /* 1-D Neumann */
 {
     if (i == 0) return f[k + st] - f[k];
@@ -242,11 +251,17 @@ void oracle_rhs(const double *mu, const double *q, const double *rho0, const dou
     size_t P = (size_t)Nx * Ny, N = P * Nt;
     double *w = (double *)malloc(3 * N * sizeof(double));
     for (size_t i = 0; i < 3 * N; i++) w[i] = mu[i] - r * q[i];
+    /* scipy's coo_matvec adds the stored entries of [Dt | Dx | Dy] one after the other into
+     * F[row]: t-block first (columns n-1, n+1), then x, then y -- one running sum. */
     for (int n = 0; n < Nt; n++)
         for (int y = 0; y < Ny; y++)
             for (int x = 0; x < Nx; x++) {
                 size_t k = IDX(n, y, x);
-                F[k] = dw(w, k, P, n, Nt) + dw(w + N, k, 1, x, Nx) + dw(w + 2 * N, k, Nx, y, Ny);
+                double s = 0.0;
+                s = dw_acc(s, w, k, P, n, Nt);
+                s = dw_acc(s, w + N, k, 1, x, Nx);
+                s = dw_acc(s, w + 2 * N, k, Nx, y, Ny);
+                F[k] = s;
             }
     for (size_t i = 0; i < P; i++) {
         double g0 = rho0[i] - mu[i] + r * q[i];
@@ -349,10 +364,14 @@ int oracle_flow_from_phi(const double *phi, int Nt, int Nx, int Ny, double *u, d
     for (int y = 0; y < Ny; y++)
         for (int x = 0; x < Nx; x++) {
             size_t k = (size_t)y * Nx + x;
-            /* div with grad_1d_central 'D': plain central, zero extension */
-            double dxu = (x + 1 < Nx ? 0.5 * u[k + 1] : 0.0) - (x > 0 ? 0.5 * u[k - 1] : 0.0);
-            double dyv = (y + 1 < Ny ? 0.5 * v[k + Nx] : 0.0) - (y > 0 ? 0.5 * v[k - Nx] : 0.0);
-            m[k] = -(dxu + dyv);
+            /* div with grad_1d_central 'D' (plain central, zero extension), accumulated the way
+             * coo_matvec does: x-block entries (x-1, x+1) then y-block entries (y-1, y+1) */
+            double s = 0.0;
+            if (x > 0) s += -0.5 * u[k - 1];
+            if (x + 1 < Nx) s += 0.5 * u[k + 1];
+            if (y > 0) s += -0.5 * v[k - Nx];
+            if (y + 1 < Ny) s += 0.5 * v[k + Nx];
+            m[k] = -s;
         }
     free(un);
     return 0;

@@ -1,0 +1,279 @@
+"""GPU: parity of the CUDA path (through the C ABI / ctypes, exactly what the shim modules call)
+against (a) golden vectors recorded from the unmodified reference and (b) the CPU oracle on the
+same seeded inputs.  Tolerances: bit-exact for index/warp/stencil-order work; the north star's
+1e-9 relative per flow component and 1e-6 px endpoint error for the fp64 solvers."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import PKG, load_golden, relerr, epe_max
+
+import foto_b200
+from foto_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ULP = 2.3e-16
+DEGENERATE = {"foto_31x29_nt2", "foto_squares32"}     # see tests/test_oracle_golden.py
+DEGENERATE_TOL = 5e-8
+
+
+def _frames(g):
+    return g["f0_u8"].astype(np.float64).ravel() / 255, g["f1_u8"].astype(np.float64).ravel() / 255
+
+
+# ----------------------------------------------------------------------------- operators
+@pytest.mark.parametrize("op", ["grad_st", "div_st", "laplacian_st", "grad", "div", "grad_forward"])
+def test_operator_apply_vs_reference(op):
+    g = load_golden("operators")
+    vec_in = {"grad_st": "N", "div_st": "3N", "laplacian_st": "N", "grad": "P", "div": "2P", "grad_forward": "P"}[op]
+    vec_out = {"grad_st": "3N", "div_st": "N", "laplacian_st": "N", "grad": "2P", "div": "P", "grad_forward": "2P"}[op]
+    n = 0
+    for k in g.files:
+        parts = k.split("/")
+        if parts[0] not in (op, op + ".T"):
+            continue
+        bc, dims, dt, dx, dy = parts[1], parts[2], float(parts[3]), float(parts[4]), float(parts[5])
+        Nt, Ny, Nx = map(int, dims.split("x"))
+        tr = parts[0].endswith(".T")
+        x = g[f"in/{dims}/{parts[3]}/{parts[4]}/{parts[5]}/" + (vec_out if tr else vec_in)]
+        y = foto_b200.op_apply(op, bc, Nt, Nx, Ny, dt, dx, dy, x, transpose=tr)
+        assert np.max(np.abs(y - g[k])) <= 16 * ULP * max(1.0, np.max(np.abs(g[k]))), k
+        n += 1
+    assert n >= 6
+
+
+# ----------------------------------------------------------------------------- stepB
+def test_stepB_all_branches_vs_reference():
+    g = load_golden("stepB")
+    Nt, Nx, Ny = map(int, g["dims"])
+    q = foto_b200.stepB(g["p"], Nt, Nx, Ny)
+    assert np.all(np.abs(q - g["q"]) <= 1e-12 * np.maximum(1.0, np.abs(g["q"])))
+
+
+def test_stepB_vs_oracle_random_and_idempotent(oracle):
+    rng = np.random.default_rng(7)
+    Nt, Ny, Nx = 3, 37, 41
+    n = Nt * Ny * Nx
+    p = rng.standard_normal(3 * n) * np.repeat([3.0, 2.0, 2.0], n)
+    p[:n // 3] -= 5.0
+    q = foto_b200.stepB(p, Nt, Nx, Ny)
+    qo = oracle.stepB(p, Nt, Nx, Ny)
+    assert np.all(np.abs(q - qo) <= 1e-12 * np.maximum(1.0, np.abs(qo)))
+    # a projection is idempotent; every output lies in K = {a + |b|^2/2 <= 0}
+    q2 = foto_b200.stepB(q, Nt, Nx, Ny)
+    assert np.max(np.abs(q2 - q)) < 1e-12
+    a, b1, b2 = q[:n], q[n:2 * n], q[2 * n:]
+    assert np.max(a + 0.5 * (b1 ** 2 + b2 ** 2)) < 1e-12
+
+
+# ----------------------------------------------------------------------------- stepA
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_stepA_vs_reference(tag):
+    g = load_golden("stepA")
+    Nt, Nx, Ny = map(int, g[f"{tag}/dims"]); r, eps = g[f"{tag}/r_eps"]
+    args = (g[f"{tag}/mu"], g[f"{tag}/q"], g[f"{tag}/rho0"], g[f"{tag}/rhoT"])
+    F = foto_b200.rhs(*args, r, Nt, Nx, Ny)
+    np.testing.assert_array_equal(F, g[f"{tag}/F"])               # K1 is bit-identical to coo_matvec
+    phi, iters, info = foto_b200.stepA(*args, r, eps, Nt, Nx, Ny)
+    assert info == 0 and iters == int(g[f"{tag}/cg_iters"][0])
+    assert relerr(phi, g[f"{tag}/phi"]) < 1e-10
+    # size-independent property: the returned phi satisfies the stopping rule ||A phi - F|| < 1e-6 ||F||
+    L = foto_b200.op_apply("laplacian_st", "N", Nt, Nx, Ny, 1, 1, 1, phi)
+    res = (-r * L + r * eps * phi) - F
+    assert np.linalg.norm(res) < 1.0001e-6 * np.linalg.norm(F)
+
+
+# ----------------------------------------------------------------------------- FOTO end to end
+FOTO = ["foto_24x32", "foto_48x64", "foto_37x53_nt5", "foto_40x56_nt16_runsh", "foto_31x29_nt2",
+        "foto_squares32", "foto_97x146"]
+
+
+@pytest.mark.parametrize("name", FOTO)
+def test_foto_solve_vs_reference(name):
+    g = load_golden(name)
+    h, w, Nt = map(int, g["dims"]); r, tol, eps, max_it = g["params"]
+    f0, f1 = _frames(g)
+    u, v, m, info = foto_b200.solve(f0, f1, Nt, w, h, r=r, convergence_tol=tol, reg_epsilon=eps, max_it=int(max_it))
+    assert info["n_outer"] == len(g["crit"])
+    np.testing.assert_array_equal(info["cg_iters"], g["cg_iters"])
+    np.testing.assert_allclose(info["crit"], g["crit"], rtol=1e-7)
+    t = DEGENERATE_TOL if name in DEGENERATE else 1e-9
+    assert relerr(u, g["u"]) < t and relerr(v, g["v"]) < t and relerr(m, g["m"]) < t
+    assert epe_max(u, v, g["u"], g["v"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["foto_24x32", "foto_48x64", "foto_37x53_nt5"])
+def test_foto_tight_backend_vs_tight_reference(name):
+    g = load_golden(name + "_tight")
+    h, w, Nt = map(int, g["dims"]); r, tol, eps, max_it = g["params"]
+    f0, f1 = _frames(g)
+    u, v, m, info = foto_b200.solve(f0, f1, Nt, w, h, r=r, convergence_tol=tol, reg_epsilon=eps,
+                                    max_it=int(max_it), backend=foto_b200.POISSON_CG_TIGHT)
+    assert info["n_outer"] == len(g["crit"])
+    assert relerr(u, g["u"]) < 1e-9 and relerr(v, g["v"]) < 1e-9 and relerr(m, g["m"]) < 1e-9
+
+
+def test_foto_full_size_vs_reference():
+    """Config 1: 388x584, CLI defaults.  The golden keeps every 13th pixel plus whole-field sums."""
+    g = load_golden("foto_388x584")
+    h, w, Nt = map(int, g["dims"])
+    f0, f1 = _frames(g)
+    u, v, m, info = foto_b200.solve(f0, f1, Nt, w, h, r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=100)
+    assert info["n_outer"] == len(g["crit"]) == 9
+    np.testing.assert_array_equal(info["cg_iters"], g["cg_iters"])
+    sub = g["sub"]
+    for name, full in (("u", u), ("v", v), ("m", m)):
+        assert relerr(full[sub], g[name]) < 1e-9, name
+        st = np.array([full.sum(), np.abs(full).sum(), np.abs(full).max(), np.sqrt((full ** 2).sum())])
+        np.testing.assert_allclose(st, g[name + "_stats"], rtol=1e-9)
+    assert epe_max(u[sub], v[sub], g["u"], g["v"]) < 1e-6
+
+
+def test_foto_vs_oracle_other_shape(oracle):
+    h, w, Nt = 61, 83, 6
+    f0, f1 = synth.make_pair(h, w, seed=11, shift=(0.3, -0.6))
+    kw = dict(r=1.3, convergence_tol=0.05, reg_epsilon=5e-3, max_it=12)
+    u, v, m, info = foto_b200.solve(f0, f1, Nt, w, h, **kw)
+    uo, vo, mo, io = oracle.solve(f0, f1, Nt, w, h, return_info=True, **kw)
+    assert info["n_outer"] == io["n_outer"]
+    np.testing.assert_array_equal(info["cg_iters"], io["cg_iters"])
+    assert relerr(u, uo) < 1e-9 and relerr(v, vo) < 1e-9 and relerr(m, mo) < 1e-9
+
+
+# ----------------------------------------------------------------------------- flow / warp
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_flow_extraction_bit_exact(tag):
+    g = load_golden("flow")
+    Nt, Nx, Ny = map(int, g[f"{tag}/dims"])
+    u, v, m = foto_b200.flow_from_phi(g[f"{tag}/phi"], Nt, Nx, Ny)
+    np.testing.assert_array_equal(u, g[f"{tag}/u"])
+    np.testing.assert_array_equal(v, g[f"{tag}/v"])
+    np.testing.assert_array_equal(m, g[f"{tag}/m"])
+
+
+def test_flow_zero_potential_gives_zero_flow():
+    u, v, m = foto_b200.flow_from_phi(np.zeros(4 * 388 * 584), 4, 584, 388)
+    assert not u.any() and not v.any() and not m.any()
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_warp_bit_exact(tag):
+    g = load_golden("warp")
+    h, w = map(int, g[f"{tag}/dims"])
+    out = foto_b200.warp_apply(g[f"{tag}/f1"], g[f"{tag}/u"], g[f"{tag}/v"], w, h, g[f"{tag}/m"])
+    np.testing.assert_array_equal(out, g[f"{tag}/out_m"])
+    out0 = foto_b200.warp_apply(g[f"{tag}/f1"], g[f"{tag}/u"], g[f"{tag}/v"], w, h, None)
+    np.testing.assert_array_equal(out0, g[f"{tag}/out_m0"])
+
+
+def test_warp_full_size_vs_oracle_and_identity(oracle):
+    h, w = 388, 584
+    rng = np.random.default_rng(3)
+    f = np.round(rng.random(h * w) * 255) / 255
+    u, v, m = rng.standard_normal(h * w) * 3, rng.standard_normal(h * w) * 3, rng.standard_normal(h * w) * 0.1
+    np.testing.assert_array_equal(foto_b200.warp_apply(f, u, v, w, h, m), oracle.warp_apply(f, u, v, w, h, m))
+    np.testing.assert_array_equal(foto_b200.warp_apply(f, np.zeros(h * w), np.zeros(h * w), w, h, None), f)
+
+
+# ----------------------------------------------------------------------------- GN
+@pytest.mark.parametrize("name", ["gn_24x32", "gn_48x64", "gn_37x53", "gn_97x146"])
+def test_gn_vs_reference(name):
+    g = load_golden(name)
+    h, w = map(int, g["dims"]); alpha, lam = g["params"]
+    f0, f1 = _frames(g)
+    if "x_probe" in g.files:
+        y, b = foto_b200.gn_system(f0, f1, w, h, alpha, lam, g["x_probe"])
+        assert relerr(y, g["Ax_probe"]) < 1e-14
+        np.testing.assert_array_equal(b, g["b"])
+    u, v, m, info = foto_b200.gn_solve(f0, f1, w, h, alpha, lam)
+    assert info["info"] == 0
+    assert relerr(u, g["u"]) < 1e-9 and relerr(v, g["v"]) < 1e-9 and relerr(m, g["m"]) < 1e-9
+    assert epe_max(u, v, g["u"], g["v"]) < 1e-6
+
+
+def test_gn_full_size_vs_reference():
+    """Config 2: 388x584, alpha 0.1, lambda 0.2 against the reference's SuperLU solution."""
+    g = load_golden("gn_388x584")
+    gf = load_golden("foto_388x584")
+    h, w = map(int, g["dims"])
+    f0, f1 = _frames(gf)
+    u, v, m, info = foto_b200.gn_solve(f0, f1, w, h, 0.1, 0.2)
+    assert info["info"] == 0
+    sub = g["sub"]
+    for name, full in (("u", u), ("v", v), ("m", m)):
+        assert relerr(full[sub], g[name]) < 1e-9, name
+        st = np.array([full.sum(), np.abs(full).sum(), np.abs(full).max(), np.sqrt((full ** 2).sum())])
+        np.testing.assert_allclose(st, g[name + "_stats"], rtol=1e-9)
+    # size-independent property: the residual of the returned solution is tiny
+    x = np.concatenate([u, v, m])
+    y, b = foto_b200.gn_system(f0, f1, w, h, 0.1, 0.2, x)
+    assert np.linalg.norm(y - b) < 1e-11 * np.linalg.norm(b)
+
+
+# ----------------------------------------------------------------------------- batch / determinism
+def test_batch_equals_single_bitwise():
+    h, w, Nt = 48, 64, 4
+    pairs = synth.make_batch(5, h, w, base_seed=20)
+    f0s = np.stack([p[0] for p in pairs]); f1s = np.stack([p[1] for p in pairs])
+    kw = dict(r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=6)
+    us, vs, ms, outer = foto_b200.solve_batch(f0s, f1s, Nt, w, h, devices=list(range(foto_b200.device_count())), **kw)
+    for i in range(len(pairs)):
+        u, v, m, info = foto_b200.solve(f0s[i], f1s[i], Nt, w, h, **kw)
+        np.testing.assert_array_equal(us[i], u); np.testing.assert_array_equal(vs[i], v)
+        np.testing.assert_array_equal(ms[i], m); assert outer[i] == info["n_outer"]
+    gu, gv, gm, it = foto_b200.gn_solve_batch(f0s, f1s, w, h, 0.1, 0.2, devices=[0])
+    u, v, m, info = foto_b200.gn_solve(f0s[2], f1s[2], w, h, 0.1, 0.2)
+    np.testing.assert_array_equal(gu[2], u); assert it[2] == info["iters"]
+
+
+# ----------------------------------------------------------------------------- shim (reference API)
+def test_shim_modules_reference_api(capsys, monkeypatch):
+    monkeypatch.syspath_prepend(os.path.join(PKG, "shim"))
+    for name in ("operators", "utils", "benamou_brenier", "classical"):
+        sys.modules.pop(name, None)
+    import benamou_brenier as bb, classical, operators, utils  # noqa: E401
+    g = load_golden("foto_24x32")
+    h, w, Nt = map(int, g["dims"])
+    f0, f1 = _frames(g)
+    u, v, m = bb.solve(f0, f1, Nt, w, h, r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=100)
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.endswith("/100)")]
+    assert len(lines) == len(g["crit"]) and lines[0].endswith("(1/100)")
+    assert abs(float(lines[-1].split(" ")[0]) - g["crit"][-1]) < 1e-7 * g["crit"][-1]
+    assert relerr(u, g["u"]) < 1e-9 and relerr(m, g["m"]) < 1e-9
+    # stepA / stepB / operators through the reference-named functions
+    gs = load_golden("stepA")
+    Nt2, Nx2, Ny2 = map(int, gs["a/dims"]); r, eps = gs["a/r_eps"]
+    from scipy import sparse
+    A = -r * operators.laplacian_st(Nt2, Nx2, Ny2, 1, 1, 1, bc='N') + r * eps * sparse.eye(Nt2 * Nx2 * Ny2)
+    D = operators.div_st(Nt2, Nx2, Ny2, 1, 1, 1, bc='N')
+    phi = bb.solve_benamou_brenier_step(gs["a/mu"], gs["a/q"], gs["a/rho0"], gs["a/rhoT"], r, A, D,
+                                        Nt2, Nx2, Ny2, 1, 1, 1)
+    assert relerr(phi, gs["a/phi"]) < 1e-10
+    np.testing.assert_array_equal(D @ (gs["a/mu"] - r * gs["a/q"]),
+                                  foto_b200.op_apply("div_st", "N", Nt2, Nx2, Ny2, 1, 1, 1, gs["a/mu"] - r * gs["a/q"]))
+    gb = load_golden("stepB")
+    q = bb.stepB(gb["p"], *map(int, gb["dims"]))
+    assert np.all(np.abs(q - gb["q"]) <= 1e-12 * np.maximum(1.0, np.abs(gb["q"])))
+    # GN class
+    gg = load_golden("gn_24x32")
+    hh, ww = map(int, gg["dims"]); f0, f1 = _frames(gg)
+    s = classical.GLLOpticalFlow(ww, hh); s.setAlpha(0.1); s.setLambda(0.2)
+    uu, vv, mm = s.assemble(f0, f1).process()
+    assert relerr(uu, gg["u"]) < 1e-9 and relerr(mm, gg["m"]) < 1e-9
+    np.testing.assert_array_equal(s.b, gg["b"])
+    assert relerr(s.A @ gg["x_probe"], gg["Ax_probe"]) < 1e-14
+    # flow + warp through utils
+    gfl = load_golden("flow")
+    Nt3, Nx3, Ny3 = map(int, gfl["a/dims"])
+    u3, v3, m3 = utils.opticalflow_from_benamoubrenier(gfl["a/phi"], Nt3, Nx3, Ny3,
+                                                       operators.grad(Nx3, Ny3, 1, 1, bc='N'),
+                                                       operators.div(Nx3, Ny3, 1, 1, bc='D'))
+    np.testing.assert_array_equal(u3, gfl["a/u"]); np.testing.assert_array_equal(m3, gfl["a/m"])
+    gw = load_golden("warp")
+    h4, w4 = map(int, gw["a/dims"])
+    np.testing.assert_array_equal(utils.apply_opticalflow(gw["a/f1"], gw["a/u"], gw["a/v"], w4, h4, gw["a/m"]), gw["a/out_m"])
+    for name in ("operators", "utils", "benamou_brenier", "classical"):
+        sys.modules.pop(name, None)
