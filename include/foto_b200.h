@@ -89,6 +89,10 @@ int  foto_ctx_set_profiling(foto_ctx *ctx, int on);         /* CUDA-event timing
 int  foto_ctx_reset_stats(foto_ctx *ctx);
 int  foto_ctx_get_stats(foto_ctx *ctx, foto_stats *out);
 int  foto_ctx_set_cg_variant(foto_ctx *ctx, int variant);   /* -1 auto, 0 streaming, 1 on-chip */
+/* CUDA-event stopwatch on the context's stream (the stream every kernel of the context is
+ * launched on): which = 0 records "start", 1 records "stop"; elapsed synchronises on "stop". */
+int  foto_ctx_event_record(foto_ctx *ctx, int which);
+int  foto_ctx_event_elapsed_ms(foto_ctx *ctx, double *ms);
 
 /* benamou_brenier.solve (benamou_brenier.py:151-271) on device buffers.
  * d_rho0, d_rhoT: P doubles; d_u, d_v, d_m: P doubles (outputs).
@@ -107,6 +111,16 @@ int  foto_solve_dev(foto_ctx *ctx, const double *d_rho0, const double *d_rhoT,
 int  foto_gn_solve_dev(foto_ctx *ctx, const double *d_f1, const double *d_f2, int w, int h,
                        double alpha, double lambda, double rtol, int max_it,
                        double *d_u, double *d_v, double *d_m, int *iters, int *info);
+
+/* Host-buffer variants on an explicit context (H2D of the inputs, solve, D2H of the results,
+ * all on the context's stream; buffers may be pageable or pinned). */
+int  foto_solve_host(foto_ctx *ctx, const double *rho0, const double *rhoT, int Nt, int Nx, int Ny,
+                     double r, double tol, double eps, int max_it, int poisson_backend,
+                     double *u, double *v, double *m,
+                     double *crit_trace, int *n_outer, int *cg_iters, int *cg_info);
+int  foto_gn_solve_host(foto_ctx *ctx, const double *f1, const double *f2, int w, int h,
+                        double alpha, double lambda, double rtol, int max_it,
+                        double *u, double *v, double *m, int *iters, int *info);
 
 /* ---- host-buffer API (what the reference's Python modules bind) ------------------- */
 /* benamou_brenier.solve, benamou_brenier.py:151 */

@@ -54,6 +54,7 @@ struct foto_ctx {
     struct Span { cudaEvent_t a, b; int cat; };
     std::vector<Span> spans;
     cudaEvent_t open_a = nullptr; int open_cat = -1;
+    cudaEvent_t watch[2] = {nullptr, nullptr};
 };
 
 static const int kProxMaxBlocks = 148 * 8;
@@ -169,6 +170,7 @@ extern "C" void foto_ctx_destroy(foto_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
+    for (auto e : c->watch) if (e) cudaEventDestroy(e);
     cudaFree(c->ws); cudaFree(c->io); cudaFree(c->sync_counter); cudaFree(c->sync_partials);
     cudaFree(c->prox_partials); cudaFree(c->d_res);
     if (c->h_res) cudaFreeHost(c->h_res);
@@ -184,6 +186,26 @@ extern "C" int foto_ctx_set_cg_variant(foto_ctx *c, int v)
 {
     if (!c || v < -1 || v > 1) { set_error("cg variant must be -1, 0 or 1"); return FOTO_ERR_ARG; }
     c->cg_variant = v;
+    return FOTO_OK;
+}
+
+extern "C" int foto_ctx_event_record(foto_ctx *c, int which)
+{
+    if (!c || which < 0 || which > 1) { set_error("foto_ctx_event_record: bad argument"); return FOTO_ERR_ARG; }
+    FOTO_TRY(ctx_bind(c));
+    if (!c->watch[which]) CUDA_TRY(cudaEventCreate(&c->watch[which]));
+    CUDA_TRY(cudaEventRecord(c->watch[which], c->stream));
+    return FOTO_OK;
+}
+
+extern "C" int foto_ctx_event_elapsed_ms(foto_ctx *c, double *ms)
+{
+    if (!c || !ms || !c->watch[0] || !c->watch[1]) { set_error("foto_ctx_event_elapsed_ms: record start and stop first"); return FOTO_ERR_ARG; }
+    FOTO_TRY(ctx_bind(c));
+    CUDA_TRY(cudaEventSynchronize(c->watch[1]));
+    float f = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&f, c->watch[0], c->watch[1]));
+    *ms = f;
     return FOTO_OK;
 }
 
@@ -403,6 +425,15 @@ extern "C" int foto_solve(const double *rho0, const double *rhoT, int Nt, int Nx
                         cg_iters, cg_info);
 }
 
+extern "C" int foto_solve_host(foto_ctx *c, const double *rho0, const double *rhoT, int Nt, int Nx, int Ny, double r,
+                               double tol, double eps, int max_it, int backend, double *u, double *v, double *m,
+                               double *crit_trace, int *n_outer, int *cg_iters, int *cg_info)
+{
+    if (!c) { set_error("foto_solve_host: NULL context"); return FOTO_ERR_ARG; }
+    return solve_on_ctx(c, rho0, rhoT, Nt, Nx, Ny, r, tol, eps, max_it, backend, u, v, m, crit_trace, n_outer,
+                        cg_iters, cg_info);
+}
+
 extern "C" int foto_stepB(const double *p, int Nt, int Nx, int Ny, double *q)
 {
     if (!p || !q) { set_error("foto_stepB: NULL argument"); return FOTO_ERR_ARG; }
@@ -603,6 +634,14 @@ extern "C" int foto_gn_solve(const double *f1, const double *f2, int w, int h, d
 {
     foto_ctx *c = nullptr;
     FOTO_TRY(default_ctx(&c));
+    return gn_on_ctx(c, f1, f2, w, h, alpha, lambda, rtol, max_it, u, v, m, iters, info);
+}
+
+extern "C" int foto_gn_solve_host(foto_ctx *c, const double *f1, const double *f2, int w, int h, double alpha,
+                                  double lambda, double rtol, int max_it, double *u, double *v, double *m, int *iters,
+                                  int *info)
+{
+    if (!c) { set_error("foto_gn_solve_host: NULL context"); return FOTO_ERR_ARG; }
     return gn_on_ctx(c, f1, f2, w, h, alpha, lambda, rtol, max_it, u, v, m, iters, info);
 }
 

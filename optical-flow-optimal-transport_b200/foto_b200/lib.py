@@ -21,7 +21,8 @@ EXPORTS = [
     "foto_last_error", "foto_version", "foto_device_count",
     "foto_ctx_create", "foto_ctx_destroy", "foto_ctx_device", "foto_ctx_set_profiling",
     "foto_ctx_reset_stats", "foto_ctx_get_stats", "foto_ctx_set_cg_variant",
-    "foto_solve_dev", "foto_gn_solve_dev",
+    "foto_ctx_event_record", "foto_ctx_event_elapsed_ms",
+    "foto_solve_dev", "foto_gn_solve_dev", "foto_solve_host", "foto_gn_solve_host",
     "foto_solve", "foto_stepB", "foto_stepA", "foto_rhs", "foto_flow_from_phi", "foto_op_apply",
     "foto_tri_coeffs", "foto_gn_solve", "foto_gn_system", "foto_warp_apply",
     "foto_solve_batch", "foto_gn_solve_batch",
@@ -287,6 +288,29 @@ class Context:
         s = Stats()
         _check(lib().foto_ctx_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def event_record(self, which):
+        _check(lib().foto_ctx_event_record(self._h, int(which)))
+
+    def event_elapsed_ms(self):
+        ms = C.c_double(0.0)
+        _check(lib().foto_ctx_event_elapsed_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def solve_host(self, rho0, rhoT, Nt, Nx, Ny, u, v, m, r=1.0, convergence_tol=0.3, reg_epsilon=1e-3,
+                   max_it=100, backend=POISSON_CG_PARITY):
+        """Host-buffer solve into preallocated numpy outputs (H2D + solve + D2H on this context)."""
+        n_outer = C.c_int(0)
+        _check(lib().foto_solve_host(self._h, _p(rho0), _p(rhoT), int(Nt), int(Nx), int(Ny), _d(r),
+                                     _d(convergence_tol), _d(reg_epsilon), int(max_it), int(backend),
+                                     _p(u), _p(v), _p(m), None, C.byref(n_outer), None, None))
+        return n_outer.value
+
+    def gn_solve_host(self, f1, f2, w, h, alpha, lam, u, v, m, rtol=0.0, max_it=0):
+        it = C.c_int(0); info = C.c_int(0)
+        _check(lib().foto_gn_solve_host(self._h, _p(f1), _p(f2), int(w), int(h), _d(alpha), _d(lam), _d(rtol),
+                                        int(max_it), _p(u), _p(v), _p(m), C.byref(it), C.byref(info)))
+        return it.value
 
     def solve_dev(self, d_rho0, d_rhoT, Nt, Nx, Ny, d_u, d_v, d_m, r=1.0, convergence_tol=0.3,
                   reg_epsilon=1e-3, max_it=100, backend=POISSON_CG_PARITY):
