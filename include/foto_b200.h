@@ -89,6 +89,11 @@ int  foto_ctx_set_profiling(foto_ctx *ctx, int on);         /* CUDA-event timing
 int  foto_ctx_reset_stats(foto_ctx *ctx);
 int  foto_ctx_get_stats(foto_ctx *ctx, foto_stats *out);
 int  foto_ctx_set_cg_variant(foto_ctx *ctx, int variant);   /* -1 auto, 0 streaming, 1 on-chip */
+/* Variant used by the contexts behind the host-buffer API (default -1 = auto; the environment
+ * variable FOTO_CG_VARIANT sets the initial value). */
+int  foto_set_default_cg_variant(int variant);
+/* Debugging aid: per-phase cycle counters of the on-chip CG kernel (see api.cu). */
+int  foto_debug_onchip_prof(foto_ctx *ctx, int enable, long long *out_1024x8);
 /* CUDA-event stopwatch on the context's stream (the stream every kernel of the context is
  * launched on): which = 0 records "start", 1 records "stop"; elapsed synchronises on "stop". */
 int  foto_ctx_event_record(foto_ctx *ctx, int which);

@@ -55,6 +55,7 @@ struct foto_ctx {
     std::vector<Span> spans;
     cudaEvent_t open_a = nullptr; int open_cat = -1;
     cudaEvent_t watch[2] = {nullptr, nullptr};
+    OnchipScratch onchip;
 };
 
 static const int kProxMaxBlocks = 148 * 8;
@@ -173,6 +174,7 @@ extern "C" void foto_ctx_destroy(foto_ctx *c)
     for (auto e : c->watch) if (e) cudaEventDestroy(e);
     cudaFree(c->ws); cudaFree(c->io); cudaFree(c->sync_counter); cudaFree(c->sync_partials);
     cudaFree(c->prox_partials); cudaFree(c->d_res);
+    cg_onchip_release(c->onchip);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -206,6 +208,26 @@ extern "C" int foto_ctx_event_elapsed_ms(foto_ctx *c, double *ms)
     float f = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&f, c->watch[0], c->watch[1]));
     *ms = f;
+    return FOTO_OK;
+}
+
+// Debugging aid: cycle counters of CTA 0 of the on-chip CG kernel, accumulated over launches:
+// [0] halo + p update, [1] stencil, [2] barrier 1, [3] r update + edge export, [4] x update,
+// [5] barrier 2 wait, [6] iterations.  enable != 0 (re)starts counting; out may be NULL.
+extern "C" int foto_debug_onchip_prof(foto_ctx *c, int enable, long long *out)
+{
+    if (!c) return FOTO_ERR_ARG;
+    FOTO_TRY(ctx_bind(c));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (out && c->onchip.prof) CUDA_TRY(cudaMemcpy(out, c->onchip.prof, 8 * 1024 * sizeof(long long), cudaMemcpyDeviceToHost));
+    else if (out) memset(out, 0, 8 * 1024 * sizeof(long long));
+    if (enable) {
+        if (!c->onchip.prof) CUDA_TRY(cudaMalloc((void **)&c->onchip.prof, 8 * 1024 * sizeof(long long)));
+        CUDA_TRY(cudaMemset(c->onchip.prof, 0, 8 * 1024 * sizeof(long long)));
+    } else if (c->onchip.prof) {
+        CUDA_TRY(cudaFree(c->onchip.prof));
+        c->onchip.prof = nullptr;
+    }
     return FOTO_OK;
 }
 
@@ -245,9 +267,11 @@ static int run_cg(foto_ctx *c, const Dims &d, const double *F, double *phi, doub
     else { set_error("unknown Poisson back-end %d", backend); return FOTO_ERR_ARG; }
     a.sync.counter = c->sync_counter; a.sync.partials = c->sync_partials; a.sync.error = &c->d_res->error;
     a.out = &c->d_res->cg_iters;
-    bool onchip = c->cg_variant == 1 || (c->cg_variant == -1 && cg_onchip_fits(c->device, d.Nt, d.Ny, d.Nx));
+    const bool fits = cg_onchip_fits(c->onchip, c->device, d.Nt, d.Ny, d.Nx);
+    if (c->cg_variant == 1 && !fits) { set_error("grid %dx%dx%d does not fit the on-chip CG variant", d.Nt, d.Ny, d.Nx); return FOTO_ERR_ARG; }
+    const bool onchip = fits && c->cg_variant != 0;
     prof_begin(c, CAT_CG);
-    if (onchip) FOTO_TRY(launch_cg_onchip(c->stream, a, c->device));
+    if (onchip) FOTO_TRY(launch_cg_onchip(c->stream, a, c->device, c->onchip));
     else FOTO_TRY(launch_cg_stream(c->stream, a, c->cg_grid, c->cg_block));
     prof_end(c);
     c->stats.cg_variant = onchip ? 1 : 0;
@@ -359,6 +383,27 @@ extern "C" int foto_gn_solve_dev(foto_ctx *c, const double *d_f1, const double *
 static std::mutex g_ctx_mutex;
 static std::map<std::pair<std::thread::id, int>, foto_ctx *> g_ctx;
 
+static std::atomic<int> g_default_variant(-2);      // -2: not yet read from the environment
+
+static int default_variant()
+{
+    int v = g_default_variant.load();
+    if (v == -2) {
+        const char *e = getenv("FOTO_CG_VARIANT");
+        v = e ? atoi(e) : -1;
+        if (v < -1 || v > 1) v = -1;
+        g_default_variant.store(v);
+    }
+    return v;
+}
+
+extern "C" int foto_set_default_cg_variant(int v)
+{
+    if (v < -1 || v > 1) { set_error("cg variant must be -1, 0 or 1"); return FOTO_ERR_ARG; }
+    g_default_variant.store(v);
+    return FOTO_OK;
+}
+
 static int default_ctx(foto_ctx **out)
 {
     int n = foto_device_count();
@@ -368,10 +413,11 @@ static int default_ctx(foto_ctx **out)
     std::lock_guard<std::mutex> lk(g_ctx_mutex);
     auto key = std::make_pair(std::this_thread::get_id(), dev);
     auto it = g_ctx.find(key);
-    if (it != g_ctx.end()) { *out = it->second; return FOTO_OK; }
+    if (it != g_ctx.end()) { *out = it->second; (*out)->cg_variant = default_variant(); return FOTO_OK; }
     foto_ctx *c = nullptr;
     FOTO_TRY(foto_ctx_create(dev, &c));
     g_ctx[key] = c;
+    c->cg_variant = default_variant();
     *out = c;
     return FOTO_OK;
 }
@@ -709,6 +755,7 @@ static int run_batch(int n_items, const int *device_ids, int n_dev, Fn per_item)
         threads.emplace_back([&, dev]() {
             foto_ctx *c = nullptr;
             int rc = foto_ctx_create(dev, &c);
+            if (rc == FOTO_OK) c->cg_variant = default_variant();
             while (rc == FOTO_OK) {
                 const int i = next.fetch_add(1);
                 if (i >= n_items || first_rc.load() != FOTO_OK) break;

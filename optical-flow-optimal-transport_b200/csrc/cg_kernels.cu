@@ -135,11 +135,4 @@ int launch_cg_stream(cudaStream_t st, const CgArgs &a, int grid, int block)
     return FOTO_OK;
 }
 
-bool cg_onchip_fits(int, int, int, int) { return false; }
-int launch_cg_onchip(cudaStream_t, const CgArgs &, int)
-{
-    set_error("on-chip CG variant not built");
-    return FOTO_ERR_ARG;
-}
-
 }  // namespace foto

@@ -50,9 +50,19 @@ struct CgArgs {
 int cg_stream_config(int device, int *grid, int *block);
 int launch_cg_stream(cudaStream_t st, const CgArgs &a, int grid, int block);
 
-// on-chip resident variant (state in shared memory/registers, one tile per SM)
-bool cg_onchip_fits(int device, int Nt, int Ny, int Nx);
-int launch_cg_onchip(cudaStream_t st, const CgArgs &a, int device);
+// on-chip resident variant (state in shared memory/registers, one tile per SM); cg_onchip.cu
+struct OnchipScratch {          // owned by the context
+    int num_sms = 0;
+    size_t smem_optin = 0;
+    double *edges = nullptr; size_t edges_bytes = 0;
+    unsigned long long *slots = nullptr;
+    long long *prof = nullptr;  // 8 cycle counters (debugging aid, see foto_debug_onchip_prof)
+    bool attr_set = false;
+    int forced_cfg = -1;        // FOTO_ONCHIP_CONFIG: pin one (threads, cells/thread) configuration
+};
+bool cg_onchip_fits(OnchipScratch &s, int device, int Nt, int Ny, int Nx);
+int launch_cg_onchip(cudaStream_t st, const CgArgs &a, int device, OnchipScratch &s);
+void cg_onchip_release(OnchipScratch &s);
 
 // ---- Gennert-Negahdaripour (gn_kernels.cu) ---------------------------------------------
 // K5: fx, fy (central, zero on the border), ft, Jacobi inverse diagonal, right-hand side

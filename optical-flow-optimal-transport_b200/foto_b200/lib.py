@@ -21,7 +21,7 @@ EXPORTS = [
     "foto_last_error", "foto_version", "foto_device_count",
     "foto_ctx_create", "foto_ctx_destroy", "foto_ctx_device", "foto_ctx_set_profiling",
     "foto_ctx_reset_stats", "foto_ctx_get_stats", "foto_ctx_set_cg_variant",
-    "foto_ctx_event_record", "foto_ctx_event_elapsed_ms",
+    "foto_ctx_event_record", "foto_ctx_event_elapsed_ms", "foto_set_default_cg_variant", "foto_debug_onchip_prof",
     "foto_solve_dev", "foto_gn_solve_dev", "foto_solve_host", "foto_gn_solve_host",
     "foto_solve", "foto_stepB", "foto_stepA", "foto_rhs", "foto_flow_from_phi", "foto_op_apply",
     "foto_tri_coeffs", "foto_gn_solve", "foto_gn_system", "foto_warp_apply",
@@ -92,6 +92,11 @@ def _check(rc):
     if rc == ERR_ARG:
         raise ValueError(msg)
     raise FotoError(rc, msg)
+
+
+def set_default_cg_variant(variant):
+    """-1 auto (on-chip CG when the grid fits, else streaming), 0 streaming, 1 on-chip."""
+    _check(lib().foto_set_default_cg_variant(int(variant)))
 
 
 def device_count():
@@ -288,6 +293,11 @@ class Context:
         s = Stats()
         _check(lib().foto_ctx_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def onchip_prof(self, enable=True):
+        out = (C.c_longlong * (8 * 1024))()
+        _check(lib().foto_debug_onchip_prof(self._h, int(bool(enable)), out))
+        return np.array(out, dtype=np.int64).reshape(1024, 8)
 
     def event_record(self, which):
         _check(lib().foto_ctx_event_record(self._h, int(which)))

@@ -20,6 +20,15 @@ DEGENERATE = {"foto_31x29_nt2", "foto_squares32"}     # see tests/test_oracle_go
 DEGENERATE_TOL = 5e-8
 
 
+@pytest.fixture(params=["onchip_or_auto", "streaming"], autouse=True)
+def cg_variant(request):
+    """Every test runs twice: with the on-chip resident CG (auto: used whenever the grid fits one
+    tile per SM) and with the streaming CG forced."""
+    foto_b200.set_default_cg_variant(0 if request.param == "streaming" else -1)
+    yield request.param
+    foto_b200.set_default_cg_variant(-1)
+
+
 def _frames(g):
     return g["f0_u8"].astype(np.float64).ravel() / 255, g["f1_u8"].astype(np.float64).ravel() / 255
 
