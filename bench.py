@@ -46,6 +46,12 @@ CPU_SAMPLE_OUTER = 2             # outer iterations timed on the CPU (of the 9 t
 EXPECTED_OUTER = 9               # measured with the reference on pair 0
 
 
+def pair_seed(rank, i):
+    """Config-1 pairs: a seeded texture and its (0.4, 0.7)-pixel translate; a different seed for
+    every pair of every rank (pair 0 of rank 0 is exactly BASELINE.md's pair)."""
+    return 1000 * rank + i
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -111,7 +117,7 @@ def _cpu_sample_worker(seed):
     """One bounded CPU sample: the first CPU_SAMPLE_OUTER outer iterations of one pair."""
     import oracle
     from foto_b200 import synth
-    f0, f1 = synth.make_pair(H, W, seed=seed)
+    f0, f1 = synth.make_pair(H, W, seed=pair_seed(0, seed))
     t0 = time.perf_counter()
     kw = dict(PARAMS)
     kw["max_it"] = CPU_SAMPLE_OUTER
@@ -185,7 +191,7 @@ def run_b200(args):
         ctx.set_cg_variant(args.cg_variant)
 
     # synthetic pairs, distinct per rank; resident in HBM before the timed region
-    pairs = synth.make_batch(B, H, W, base_seed=100 * rank)
+    pairs = [synth.make_pair(H, W, seed=pair_seed(rank, i)) for i in range(B)]
     h0 = torch.empty((B, P), dtype=torch.float64).pin_memory()
     h1 = torch.empty((B, P), dtype=torch.float64).pin_memory()
     for i, (a, b) in enumerate(pairs):
@@ -196,10 +202,10 @@ def run_b200(args):
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     torch.cuda.synchronize()
 
+    from foto_b200 import shard
+
     def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
+        shard.barrier()
         torch.cuda.synchronize()
 
     outer_counts = []
@@ -259,13 +265,8 @@ def run_b200(args):
     gn_ms = ctx.event_elapsed_ms()
     barrier()
 
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([dev_ms, e2e_s * 1e3, gn_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms, gn_ms = (float(x) for x in t.tolist())
-    else:
-        e2e_ms = e2e_s * 1e3
+    # device times: max over ranks (no-op without a process group)
+    dev_ms, e2e_ms, gn_ms = shard.max_over_ranks([dev_ms, e2e_s * 1e3, gn_ms], device=dev)
 
     if rank == 0:
         peak, peak_src = peaks()

@@ -286,3 +286,54 @@ def test_shim_modules_reference_api(capsys, monkeypatch):
     np.testing.assert_array_equal(utils.apply_opticalflow(gw["a/f1"], gw["a/u"], gw["a/v"], w4, h4, gw["a/m"]), gw["a/out_m"])
     for name in ("operators", "utils", "benamou_brenier", "classical"):
         sys.modules.pop(name, None)
+
+
+# ----------------------------------------------------------------------------- CLI pipeline
+def test_cli_pipeline_flo_output(tmp_path, monkeypatch, oracle, capsys):
+    """The sequence main.py runs (main.py:52-53,93,110-111,136-138): PNG -> solve -> warp -> IE -> .flo,
+    through the shim modules; the .flo payload must equal the oracle's flow cast to float32."""
+    from PIL import Image
+    monkeypatch.syspath_prepend(os.path.join(PKG, "shim"))
+    for name in ("operators", "utils", "benamou_brenier", "classical"):
+        sys.modules.pop(name, None)
+    import benamou_brenier as bb, utils  # noqa: E401
+    h, w, Nt = 40, 56, 4
+    f0, f1 = synth.make_pair(h, w, seed=9)
+    for name, f in (("f0.png", f0), ("f1.png", f1)):
+        Image.fromarray(np.uint8(np.round(255 * f)).reshape(h, w), "L").save(str(tmp_path / name))
+    a, ww, hh = utils.openGrayscaleImage(str(tmp_path / "f0.png"))
+    b, _, _ = utils.openGrayscaleImage(str(tmp_path / "f1.png"))
+    assert (ww, hh) == (w, h)
+    np.testing.assert_array_equal(a, f0)
+    u, v, m = bb.solve(a, b, Nt, ww, hh, r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=100)
+    rec = np.clip(utils.apply_opticalflow(a, u, v, ww, hh, m), 0, 1)
+    ie = utils.IE(ww, hh, rec, b)
+    utils.saveFlo(ww, hh, u, v, str(tmp_path / "out.flo"))
+    uo, vo, mo = oracle.solve(f0, f1, Nt, w, h, r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=100)
+    ie_o = utils.IE(w, h, np.clip(oracle.warp_apply(f0, uo, vo, w, h, mo), 0, 1), f1)
+    assert abs(ie - ie_o) < 1e-8 * max(1.0, ie_o)
+    w2, h2, uf, vf = utils.openFlo(str(tmp_path / "out.flo"))
+    assert (w2, h2) == (w, h)
+    np.testing.assert_allclose(uf, uo.astype(np.float32), rtol=0, atol=1e-7 * np.abs(uo).max())
+    np.testing.assert_allclose(vf, vo.astype(np.float32), rtol=0, atol=1e-7 * np.abs(vo).max())
+    for name in ("operators", "utils", "benamou_brenier", "classical"):
+        sys.modules.pop(name, None)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/main.py"), reason="the reference checkout is only in the build container")
+def test_reference_cli_runs_against_shim(tmp_path):
+    """The UNMODIFIED reference main.py against the shim directory (needs the reference AND a GPU)."""
+    import subprocess
+    from PIL import Image
+    h, w = 24, 32
+    f0, f1 = synth.make_pair(h, w, seed=1)
+    for name, f in (("f0.png", f0), ("f1.png", f1)):
+        Image.fromarray(np.uint8(np.round(255 * f)).reshape(h, w), "L").save(str(tmp_path / name))
+    code = ("import runpy, sys; sys.path.insert(0, %r); sys.argv = ['main.py', %r, %r, '--algo=foto', '--out', %r]; "
+            "runpy.run_path('/root/reference/main.py', run_name='__main__')"
+            % (os.path.join(PKG, "shim"), str(tmp_path / "f0.png"), str(tmp_path / "f1.png"), str(tmp_path / "o.flo")))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    g = load_golden("foto_24x32")
+    raw = np.fromfile(str(tmp_path / "o.flo"), np.float32)[3:].reshape(-1, 2)
+    np.testing.assert_allclose(raw[:, 0], g["u"].astype(np.float32), atol=1e-7)
