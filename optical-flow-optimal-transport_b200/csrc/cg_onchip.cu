@@ -430,6 +430,7 @@ Plan make_plan(OnchipScratch &d, int device, int Nt, int Ny, int Nx)
                 }
             }
         }
+        if (best.ok) break;        // configurations are listed fastest first: take the first that fits
     }
     return best;
 }
