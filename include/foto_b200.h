@@ -38,6 +38,8 @@ extern "C" {
 /* Poisson back-ends for stepA (parity trap #1) */
 #define FOTO_POISSON_CG_PARITY  0   /* scipy.sparse.linalg.cg recurrence, rtol 1e-6, maxiter 1000, x0 = 0 */
 #define FOTO_POISSON_CG_TIGHT   1   /* same recurrence, rtol 1e-13, maxiter 100000 ("tight" oracle)      */
+#define FOTO_POISSON_DCT_EXACT  2   /* exact solve by separable DCT-II/III (dense fp64 transforms); agrees
+                                       with CG_TIGHT to ~1e-12, NOT with the reference's truncated CG     */
 
 /* operator ids for foto_op_apply (reference operators.py) */
 #define FOTO_OP_GRAD_ST         0   /* operators.py:114-127   N  -> 3N */

@@ -56,6 +56,7 @@ struct foto_ctx {
     cudaEvent_t open_a = nullptr; int open_cat = -1;
     cudaEvent_t watch[2] = {nullptr, nullptr};
     OnchipScratch onchip;
+    DctTables dct;
 };
 
 static const int kProxMaxBlocks = 148 * 8;
@@ -175,6 +176,7 @@ extern "C" void foto_ctx_destroy(foto_ctx *c)
     cudaFree(c->ws); cudaFree(c->io); cudaFree(c->sync_counter); cudaFree(c->sync_partials);
     cudaFree(c->prox_partials); cudaFree(c->d_res);
     cg_onchip_release(c->onchip);
+    cudaFree(c->dct.base);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -253,10 +255,48 @@ static int fetch_result(foto_ctx *c)
     return FOTO_OK;
 }
 
+static int ensure_dct_tables(foto_ctx *c, const Dims &d)
+{
+    DctTables &t = c->dct;
+    if (t.base && t.Nt == d.Nt && t.Ny == d.Ny && t.Nx == d.Nx) return FOTO_OK;
+    if (t.base) { CUDA_TRY(cudaFree(t.base)); t = DctTables(); }
+    const int n[3] = {d.Nx, d.Ny, d.Nt};
+    size_t total = 0;
+    for (int a = 0; a < 3; a++) total += 2 * (size_t)n[a] * n[a] + n[a];
+    std::vector<double> host; host.reserve(total);
+    std::vector<size_t> off;
+    for (int a = 0; a < 3; a++) {
+        std::vector<double> C, Ct, lam;
+        dct_host_tables(n[a], C, Ct, lam);
+        off.push_back(host.size()); host.insert(host.end(), C.begin(), C.end());
+        off.push_back(host.size()); host.insert(host.end(), Ct.begin(), Ct.end());
+        off.push_back(host.size()); host.insert(host.end(), lam.begin(), lam.end());
+    }
+    CUDA_TRY(cudaMalloc((void **)&t.base, total * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(t.base, host.data(), total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));          // host vector goes out of scope
+    t.Cx = t.base + off[0]; t.CxT = t.base + off[1]; t.lam_x = t.base + off[2];
+    t.Cy = t.base + off[3]; t.CyT = t.base + off[4]; t.lam_y = t.base + off[5];
+    t.Ct = t.base + off[6]; t.CtT = t.base + off[7]; t.lam_t = t.base + off[8];
+    t.Nt = d.Nt; t.Ny = d.Ny; t.Nx = d.Nx;
+    return FOTO_OK;
+}
+
 // One Poisson solve A phi = F on device buffers.  work: 4N doubles (r, p0, p1, q).
 static int run_cg(foto_ctx *c, const Dims &d, const double *F, double *phi, double *work, double r, double eps,
                   int backend)
 {
+    if (backend == FOTO_POISSON_DCT_EXACT) {
+        FOTO_TRY(ensure_dct_tables(c, d));
+        prof_begin(c, CAT_CG);
+        FOTO_TRY(launch_poisson_dct(c->stream, c->dct, d.Nt, d.Ny, d.Nx, r, eps, F, phi, work, work + d.N));
+        prof_end(c);
+        // report "0 iterations, converged" through the same result block the CG kernels write
+        CUDA_TRY(cudaMemsetAsync(&c->d_res->cg_iters, 0, 2 * sizeof(int), c->stream));
+        c->stats.cg_variant = 2;
+        c->stats.launches += 7; c->stats.cg_launches++;
+        return FOTO_OK;
+    }
     CgArgs a;
     a.b = F; a.x = phi;
     a.r = work; a.p0 = work + d.N; a.p1 = work + 2ull * d.N; a.q = work + 3ull * d.N;

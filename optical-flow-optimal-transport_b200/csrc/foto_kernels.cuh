@@ -64,6 +64,17 @@ bool cg_onchip_fits(OnchipScratch &s, int device, int Nt, int Ny, int Nx);
 int launch_cg_onchip(cudaStream_t st, const CgArgs &a, int device, OnchipScratch &s);
 void cg_onchip_release(OnchipScratch &s);
 
+// ---- exact Poisson solve by separable DCT (dct_kernels.cu) -------------------------------
+struct DctTables {              // device pointers, owned by the context, valid for (Nt, Ny, Nx)
+    int Nt = 0, Ny = 0, Nx = 0;
+    double *base = nullptr;     // one allocation holding everything below
+    double *Cx = nullptr, *CxT = nullptr, *Cy = nullptr, *CyT = nullptr, *Ct = nullptr, *CtT = nullptr;
+    double *lam_x = nullptr, *lam_y = nullptr, *lam_t = nullptr;
+};
+void dct_host_tables(int n, std::vector<double> &C, std::vector<double> &Ct, std::vector<double> &lam);
+int launch_poisson_dct(cudaStream_t st, const DctTables &tb, int Nt, int Ny, int Nx, double r, double eps,
+                       const double *F, double *phi, double *w0, double *w1);
+
 // ---- Gennert-Negahdaripour (gn_kernels.cu) ---------------------------------------------
 // K5: fx, fy (central, zero on the border), ft, Jacobi inverse diagonal, right-hand side
 void launch_gn_coeffs(cudaStream_t st, int w, int h, const double *f1, const double *f2, double alpha,

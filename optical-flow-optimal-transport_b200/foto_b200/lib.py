@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libfoto_b200.so")
 _CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 
-POISSON_CG_PARITY, POISSON_CG_TIGHT = 0, 1
+POISSON_CG_PARITY, POISSON_CG_TIGHT, POISSON_DCT_EXACT = 0, 1, 2
 OPS = {"grad_st": 0, "div_st": 1, "laplacian_st": 2, "grad": 3, "div": 4, "grad_forward": 5}
 KINDS = {"grad_1d_forward_weird": 0, "grad_1d_backward_weird": 1, "grad_1d_central_weird": 2,
          "grad_1d_central": 3, "grad_1d_forward": 4, "grad_1d_backward": 5, "lap1d": 6}

@@ -337,3 +337,48 @@ def test_reference_cli_runs_against_shim(tmp_path):
     g = load_golden("foto_24x32")
     raw = np.fromfile(str(tmp_path / "o.flo"), np.float32)[3:].reshape(-1, 2)
     np.testing.assert_allclose(raw[:, 0], g["u"].astype(np.float32), atol=1e-7)
+
+
+# ----------------------------------------------------------------------------- dct_exact back-end (K2b)
+@pytest.mark.parametrize("name", ["foto_24x32", "foto_48x64", "foto_37x53_nt5"])
+def test_dct_exact_vs_tight_reference(name):
+    """Exact DCT Poisson solve against the reference run with its inner CG at rtol 1e-13."""
+    g = load_golden(name + "_tight")
+    h, w, Nt = map(int, g["dims"]); r, tol, eps, max_it = g["params"]
+    f0, f1 = _frames(g)
+    u, v, m, info = foto_b200.solve(f0, f1, Nt, w, h, r=r, convergence_tol=tol, reg_epsilon=eps,
+                                    max_it=int(max_it), backend=foto_b200.POISSON_DCT_EXACT)
+    assert info["n_outer"] == len(g["crit"])
+    np.testing.assert_allclose(info["crit"], g["crit"], rtol=1e-7)
+    assert relerr(u, g["u"]) < 1e-9 and relerr(v, g["v"]) < 1e-9 and relerr(m, g["m"]) < 1e-9
+    assert epe_max(u, v, g["u"], g["v"]) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_stepA_dct_exact_solves_the_system(tag):
+    g = load_golden("stepA")
+    Nt, Nx, Ny = map(int, g[f"{tag}/dims"]); r, eps = g[f"{tag}/r_eps"]
+    args = (g[f"{tag}/mu"], g[f"{tag}/q"], g[f"{tag}/rho0"], g[f"{tag}/rhoT"])
+    phi, iters, info = foto_b200.stepA(*args, r, eps, Nt, Nx, Ny, backend=foto_b200.POISSON_DCT_EXACT)
+    assert iters == 0 and info == 0
+    F = g[f"{tag}/F"]
+    L = foto_b200.op_apply("laplacian_st", "N", Nt, Nx, Ny, 1, 1, 1, phi)
+    assert np.linalg.norm((-r * L + r * eps * phi) - F) < 1e-11 * np.linalg.norm(F)
+    phi_t, _, _ = foto_b200.stepA(*args, r, eps, Nt, Nx, Ny, backend=foto_b200.POISSON_CG_TIGHT)
+    assert relerr(phi, phi_t) < 1e-9
+    # the reference's truncated CG differs from the exact solve at the 1e-6 level, by construction
+    assert 1e-9 < relerr(phi, g[f"{tag}/phi"]) < 1e-3
+
+
+def test_dct_exact_full_size_matches_tight_cg():
+    g = load_golden("foto_388x584")
+    h, w, Nt = map(int, g["dims"])
+    f0, f1 = _frames(g)
+    kw = dict(r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=100)
+    u, v, m, info = foto_b200.solve(f0, f1, Nt, w, h, backend=foto_b200.POISSON_DCT_EXACT, **kw)
+    ut, vt, mt, it = foto_b200.solve(f0, f1, Nt, w, h, backend=foto_b200.POISSON_CG_TIGHT, **kw)
+    assert info["n_outer"] == it["n_outer"]
+    assert relerr(u, ut) < 1e-9 and relerr(v, vt) < 1e-9 and relerr(m, mt) < 1e-9
+    # and stays within the 1e-6 px endpoint-error contract of the as-shipped reference
+    sub = g["sub"]
+    assert epe_max(u[sub], v[sub], g["u"], g["v"]) < 1e-6
