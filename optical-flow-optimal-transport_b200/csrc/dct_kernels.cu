@@ -10,11 +10,8 @@
 // opt-in back-end (FOTO_POISSON_DCT_EXACT), gated against the "tight" goldens (the reference
 // with its inner CG run to rtol 1e-13), never the default.
 //
-// Transforms are batched dense fp64 GEMMs on the CUDA cores (584 = 8*73 and 388 = 4*97 are
-// FFT-hostile; 3.5 GFLOP per solve at 388x584x4).  B200's fp64 tensor (DMMA) peak equals its
-// DFMA peak, so tensor cores would not raise the roof of this kernel; the register-tiled kernel
-// below keeps the fp64 pipe, not shared memory, as the limiter (6 shared-memory wavefronts
-// against 32 fp64 issue cycles per k-step and warp).
+// Transforms are batched dense fp64 GEMMs (584 = 8*73 and 388 = 4*97 are FFT-hostile; 3.5 GFLOP
+// per solve at 388x584x4) on the fp64 tensor-core MMA (m8n8k4, SASS DMMA): see k_dgemm_nn.
 #include <cmath>
 
 #include "foto_kernels.cuh"
@@ -23,80 +20,136 @@ namespace foto {
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;     // 256 threads, 4x4 outputs each
+constexpr int BM = 64, BN = 64, BK = 16, GT = 128, STAGES = 2;   // 4 warps, each a 32x32 output tile
+constexpr int APITCH = BK + 4;       // = 4 (mod 16): the 8x4 A fragment of a half-warp hits 16 distinct bank pairs
+constexpr int BPITCH = BN + 4;       // = 4 (mod 16): same for the 4x8 B fragment
 
-// C[b] = A[b] * B[b], row-major, A: M x K (lda), B: K x N (ldb), C: M x N (ldc); batch strides in doubles
-__global__ void __launch_bounds__(256) k_dgemm_nn(int M, int N, int K, const double *__restrict__ A, int lda,
-                                                   long long strideA, const double *__restrict__ B, int ldb,
-                                                   long long strideB, double *__restrict__ C, int ldc, long long strideC)
+// 8-byte asynchronous global -> shared copy (LDGSTS), zero-filled when !valid
+__device__ __forceinline__ void cp_async8(double *dst, const double *src, bool valid)
 {
-    __shared__ __align__(16) double As[2][BK][BM + 4];      // As[k][m] (transposed on load)
-    __shared__ __align__(16) double Bs[2][BK][BN];
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst);
+    const int bytes = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+
+// D(8x8) += A(8x4, row) * B(4x8, col), fp64 tensor-core MMA (SASS: DMMA)
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// C[b] = A[b] * B[b], row-major, A: M x K (lda), B: K x N (ldb), C: M x N (ldc); batch strides in doubles.
+// A register-tiled CUDA-core version of this kernel (4x4 outputs per thread) ran at 17 % of the fp64
+// peak with the shared-memory pipe 50-58 % busy (ncu): operand delivery, not the fp64 pipe, was the
+// limit.  The m8n8k4 fp64 MMA shares each operand across the warp inside the tensor-core datapath:
+// a warp tile of 32x32 needs 8 shared-memory doubles per thread for 128 FMAs per thread (the 4x4
+// CUDA-core tile: 8 doubles for 16 FMAs).  Operand tiles travel global -> shared with cp.async, one
+// k-tile ahead of the MMAs.
+__global__ void __launch_bounds__(GT) k_dgemm_nn(int M, int N, int K, const double *__restrict__ A, int lda,
+                                                  long long strideA, const double *__restrict__ B, int ldb,
+                                                  long long strideB, double *__restrict__ C, int ldc, long long strideC)
+{
+    __shared__ __align__(16) double As[STAGES][BM][APITCH];   // As[m][k]
+    __shared__ __align__(16) double Bs[STAGES][BK][BPITCH];   // Bs[k][n]
     A += (size_t)blockIdx.z * strideA; B += (size_t)blockIdx.z * strideB; C += (size_t)blockIdx.z * strideC;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;          // thread tile: rows ty*4.., cols tx*4..
-    double acc[TM][TN];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;              // warp tile origin inside the block tile
+    const int fr = lane >> 2, fc = lane & 3;                            // fragment row / column of this lane
+    double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < TM; i++)
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < TN; j++) acc[i][j] = 0.0;
+        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-    // loaders: A tile 64 x 16 (each thread 4 elements: row = tid/4, cols (tid%4)*4..), B tile 16 x 64
-    const int ar = tid >> 2, ac = (tid & 3) * 4;
-    const int br = tid >> 4, bc = (tid & 15) * 4;
-    auto load_tiles = [&](int buf, int k0) {
+    // A tile 64 x 16: 8 passes of (row = pass*8 + tid/16, k = tid%16); B tile 16 x 64: 8 passes of (row = pass*2 + tid/64, col = tid%64)
+    auto prefetch = [&](int stage, int k0) {
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int gm = m0 + ar, gk = k0 + ac + e;
-            As[buf][ac + e][ar] = (gm < M && gk < K) ? A[(size_t)gm * lda + gk] : 0.0;
+        for (int ps = 0; ps < 8; ps++) {
+            const int r = ps * 8 + (tid >> 4), c = tid & 15;
+            const int gm = m0 + r, gk = k0 + c;
+            const bool ok = gm < M && gk < K;
+            cp_async8(&As[stage][r][c], ok ? A + (size_t)gm * lda + gk : A, ok);
         }
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int gk = k0 + br, gn = n0 + bc + e;
-            Bs[buf][br][bc + e] = (gk < K && gn < N) ? B[(size_t)gk * ldb + gn] : 0.0;
+        for (int ps = 0; ps < 8; ps++) {
+            const int r = ps * 2 + (tid >> 6), c = tid & 63;
+            const int gk = k0 + r, gn = n0 + c;
+            const bool ok = gk < K && gn < N;
+            cp_async8(&Bs[stage][r][c], ok ? B + (size_t)gk * ldb + gn : B, ok);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    load_tiles(0, 0);
-    __syncthreads();
     const int nk = (K + BK - 1) / BK;
+    prefetch(0, 0);
     for (int kt = 0; kt < nk; kt++) {
-        const int buf = kt & 1;
-        if (kt + 1 < nk) load_tiles(buf ^ 1, (kt + 1) * BK);
-#pragma unroll
-        for (int k = 0; k < BK; k++) {
-            double a[TM], b[TN];
-#pragma unroll
-            for (int i = 0; i < TM; i++) a[i] = As[buf][k][ty * TM + i];
-#pragma unroll
-            for (int j = 0; j < TN; j++) b[j] = Bs[buf][k][tx * TN + j];
-#pragma unroll
-            for (int i = 0; i < TM; i++)
-#pragma unroll
-                for (int j = 0; j < TN; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-        }
+        const int st = kt & 1;
+        if (kt + 1 < nk) prefetch(st ^ 1, (kt + 1) * BK); else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");     // k-tile kt has landed
         __syncthreads();
+#pragma unroll
+        for (int k4 = 0; k4 < BK; k4 += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[st][wm + i * 8 + fr][k4 + fc];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = Bs[st][k4 + fc][wn + j * 8 + fr];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncthreads();                                          // stage st may be overwritten by the next prefetch
     }
 #pragma unroll
-    for (int i = 0; i < TM; i++) {
-        const int gm = m0 + ty * TM + i;
+    for (int i = 0; i < 4; i++) {
+        const int gm = m0 + wm + i * 8 + fr;
         if (gm >= M) continue;
 #pragma unroll
-        for (int j = 0; j < TN; j++) {
-            const int gn = n0 + tx * TN + j;
-            if (gn < N) C[(size_t)gm * ldc + gn] = acc[i][j];
+        for (int j = 0; j < 4; j++) {
+            const int gn = n0 + wn + j * 8 + fc * 2;
+            if (gn < N) C[(size_t)gm * ldc + gn] = acc[i][j][0];
+            if (gn + 1 < N) C[(size_t)gm * ldc + gn + 1] = acc[i][j][1];
         }
     }
 }
 
-// divide the spectrum by the eigenvalues of A: r (eps + lam_t[a] + lam_y[b] + lam_x[c])
-__global__ void __launch_bounds__(256) k_spectral_divide(int Nt, int Ny, int Nx, double r, double eps,
-                                                          const double *__restrict__ lam_t, const double *__restrict__ lam_y,
-                                                          const double *__restrict__ lam_x, double *__restrict__ v)
+// Forward t-DCT, division by the eigenvalues r (eps + lam_t[a] + lam_y[b] + lam_x[c]) and inverse
+// t-DCT fused into one pass: one thread per (y, x) spectral column, Nt values in registers.
+template <int MAXNT>
+__global__ void __launch_bounds__(256) k_t_solve(int Nt, int Ny, int Nx, double r, double eps,
+                                                  const double *__restrict__ Ct, const double *__restrict__ lam_t,
+                                                  const double *__restrict__ lam_y, const double *__restrict__ lam_x,
+                                                  const double *__restrict__ in, double *__restrict__ out)
 {
-    const unsigned int N = (unsigned int)Nt * Ny * Nx, stride = gridDim.x * blockDim.x;
-    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += stride) {
-        const unsigned int row = k / (unsigned int)Nx, x = k - row * Nx, t = row / (unsigned int)Ny, y = row - t * Ny;
-        v[k] = v[k] / (r * (eps + lam_t[t] + lam_y[y] + lam_x[x]));
+    __shared__ double sC[MAXNT * MAXNT], sl[MAXNT];
+    for (int i = threadIdx.x; i < Nt * Nt; i += blockDim.x) sC[i] = Ct[i];
+    for (int i = threadIdx.x; i < Nt; i += blockDim.x) sl[i] = lam_t[i];
+    __syncthreads();
+    const unsigned int P = (unsigned int)Ny * Nx;
+    const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P) return;
+    const unsigned int y = k / (unsigned int)Nx, x = k - y * Nx;
+    const double lyx = lam_y[y] + lam_x[x];
+    double v[MAXNT], w[MAXNT];
+#pragma unroll
+    for (int n = 0; n < MAXNT; n++) v[n] = n < Nt ? in[(size_t)n * P + k] : 0.0;
+#pragma unroll
+    for (int a = 0; a < MAXNT; a++) {
+        double s = 0.0;
+#pragma unroll
+        for (int n = 0; n < MAXNT; n++) if (n < Nt) s = fma(sC[a * Nt + n], v[n], s);
+        w[a] = a < Nt ? s / (r * (eps + sl[a] + lyx)) : 0.0;
+    }
+#pragma unroll
+    for (int n = 0; n < MAXNT; n++) {
+        if (n < Nt) {
+            double s = 0.0;
+#pragma unroll
+            for (int a = 0; a < MAXNT; a++) if (a < Nt) s = fma(sC[a * Nt + n], w[a], s);
+            out[(size_t)n * P + k] = s;
+        }
     }
 }
 
@@ -126,11 +179,11 @@ static void gemm(cudaStream_t st, int M, int N, int K, const double *A, int lda,
                  long long sB, double *C, int ldc, long long sC, int batch)
 {
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch);
-    k_dgemm_nn<<<grid, 256, 0, st>>>(M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC);
+    k_dgemm_nn<<<grid, GT, 0, st>>>(M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC);
 }
 
 // phi = A^-1 F.  tabs: device tables for this grid; w0, w1: two N-double scratch volumes.
-// 7 launches: x, y, t forward transforms, spectral divide, t, y, x inverse transforms.
+// 5 launches: x, y forward transforms; fused t-transform / divide / inverse t; y, x inverse transforms.
 int launch_poisson_dct(cudaStream_t st, const DctTables &tb, int Nt, int Ny, int Nx, double r, double eps,
                        const double *F, double *phi, double *w0, double *w1)
 {
@@ -138,12 +191,18 @@ int launch_poisson_dct(cudaStream_t st, const DctTables &tb, int Nt, int Ny, int
     // forward: rows * Cx^T  (M = Nt*Ny, K = Nx),   Cy * plane (batched over t),   Ct * [Nt x P]
     gemm(st, Nt * Ny, Nx, Nx, F, Nx, 0, tb.CxT, Nx, 0, w0, Nx, 0, 1);
     gemm(st, Ny, Nx, Ny, tb.Cy, Ny, 0, w0, Nx, P, w1, Nx, P, Nt);
-    gemm(st, Nt, (int)P, Nt, tb.Ct, Nt, 0, w1, (int)P, 0, w0, (int)P, 0, 1);
-    k_spectral_divide<<<148 * 8, 256, 0, st>>>(Nt, Ny, Nx, r, eps, tb.lam_t, tb.lam_y, tb.lam_x, w0);
+    {
+        const int blocks = (int)((P + 255) / 256);
+        if (Nt <= 4) k_t_solve<4><<<blocks, 256, 0, st>>>(Nt, Ny, Nx, r, eps, tb.Ct, tb.lam_t, tb.lam_y, tb.lam_x, w1, w0);
+        else if (Nt <= 8) k_t_solve<8><<<blocks, 256, 0, st>>>(Nt, Ny, Nx, r, eps, tb.Ct, tb.lam_t, tb.lam_y, tb.lam_x, w1, w0);
+        else if (Nt <= 16) k_t_solve<16><<<blocks, 256, 0, st>>>(Nt, Ny, Nx, r, eps, tb.Ct, tb.lam_t, tb.lam_y, tb.lam_x, w1, w0);
+        else if (Nt <= 32) k_t_solve<32><<<blocks, 256, 0, st>>>(Nt, Ny, Nx, r, eps, tb.Ct, tb.lam_t, tb.lam_y, tb.lam_x, w1, w0);
+        else if (Nt <= 64) k_t_solve<64><<<blocks, 256, 0, st>>>(Nt, Ny, Nx, r, eps, tb.Ct, tb.lam_t, tb.lam_y, tb.lam_x, w1, w0);
+        else { set_error("dct_exact supports Nt <= 64"); return FOTO_ERR_ARG; }
+    }
     // inverse (DCT-III = transpose)
-    gemm(st, Nt, (int)P, Nt, tb.CtT, Nt, 0, w0, (int)P, 0, w1, (int)P, 0, 1);
-    gemm(st, Ny, Nx, Ny, tb.CyT, Ny, 0, w1, Nx, P, w0, Nx, P, Nt);
-    gemm(st, Nt * Ny, Nx, Nx, w0, Nx, 0, tb.Cx, Nx, 0, phi, Nx, 0, 1);
+    gemm(st, Ny, Nx, Ny, tb.CyT, Ny, 0, w0, Nx, P, w1, Nx, P, Nt);
+    gemm(st, Nt * Ny, Nx, Nx, w1, Nx, 0, tb.Cx, Nx, 0, phi, Nx, 0, 1);
     CUDA_TRY(cudaGetLastError());
     return FOTO_OK;
 }
