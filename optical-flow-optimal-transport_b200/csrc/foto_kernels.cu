@@ -67,22 +67,32 @@ __device__ __forceinline__ double dw_acc(double s, const double *__restrict__ mu
     return s;
 }
 
-__global__ void __launch_bounds__(kThreads) k_rhs(Dims d, const double *__restrict__ mu, const double *__restrict__ q,
+// One thread per (y, x) column marching through t: w_t = (mu - r q)_rho of the planes n-1, n, n+1
+// stays in registers, so every word of mu and q is read once from HBM even when a plane (16 MB at
+// 1080x1920) is far larger than what L2 keeps between two visits.
+__global__ void __launch_bounds__(kThreads, 8) k_rhs(Dims d, const double *__restrict__ mu, const double *__restrict__ q,
                                                    const double *__restrict__ rho0, const double *__restrict__ rhoT,
                                                    double r, double *__restrict__ F)
 {
     const unsigned int stride = gridDim.x * blockDim.x;
-    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < d.N; k += stride) {
-        int n, y, x;
-        decode(k, d, n, y, x);
-        double s = 0.0;
-        s = dw_acc(s, mu, q, r, k, d.P, n, d.Nt);
-        s = dw_acc(s, mu + d.N, q + d.N, r, k, 1u, x, d.Nx);
-        s = dw_acc(s, mu + 2u * d.N, q + 2u * d.N, r, k, (unsigned int)d.Nx, y, d.Ny);
-        unsigned int i = k - (unsigned int)n * d.P;
-        if (n == 0) s -= (rho0[i] - mu[k] + r * q[k]);
-        if (n == d.Nt - 1) s += (rhoT[i] - mu[k] + r * q[k]);
-        F[k] = s;
+    const double *mu1 = mu + d.N, *q1 = q + d.N, *mu2 = mu + 2u * d.N, *q2 = q + 2u * d.N;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.P; i += stride) {
+        const int y = (int)(i / (unsigned int)d.Nx), x = (int)(i - (unsigned int)y * d.Nx);
+        double w_m = 0.0, w_c = wv(mu, q, r, i), w_p = wv(mu, q, r, d.P + i);
+        for (int n = 0; n < d.Nt; n++) {
+            const unsigned int k = (unsigned int)n * d.P + i;
+            double s = 0.0;
+            if (n == 0) { s += -1.0 * w_c; s += 1.0 * w_p; }
+            else if (n == d.Nt - 1) { s += -1.0 * w_m; s += 1.0 * w_c; }
+            else { s += -0.5 * w_m; s += 0.5 * w_p; }
+            s = dw_acc(s, mu1, q1, r, k, 1u, x, d.Nx);
+            s = dw_acc(s, mu2, q2, r, k, (unsigned int)d.Nx, y, d.Ny);
+            if (n == 0) s -= (rho0[i] - mu[k] + r * q[k]);
+            if (n == d.Nt - 1) s += (rhoT[i] - mu[k] + r * q[k]);
+            F[k] = s;
+            w_m = w_c; w_c = w_p;
+            if (n + 2 < d.Nt) w_p = wv(mu, q, r, k + 2u * d.P);
+        }
     }
 }
 
@@ -95,15 +105,23 @@ __device__ __forceinline__ void project_K(double a, double b1, double b2, double
 {
     const double rho2 = b1 * b1 + b2 * b2;
     if (2.0 * a + rho2 <= 0.0) { qa = a; qb1 = b1; qb2 = b2; return; }
-    const double rho = sqrt(rho2);
+    // One rsqrt gives rho and the direction (cos, sin) = (b1, b2)/rho; atan2(0, 0) = 0 -> (1, 0).
+    // K3 is fp64-instruction bound, not HBM bound, when written with sqrt + two divisions here and
+    // cbrt + a division below (52 % of the HBM roofline at 1080x1920x16); rsqrt/rcbrt halve the count.
+    double rho = 0.0, ct = 1.0, st = 0.0;
+    if (rho2 > 0.0) {
+        const double rinv = rsqrt(rho2);
+        rho = rho2 * rinv; ct = b1 * rinv; st = b2 * rinv;
+    }
     const double a1 = a + 1.0;
     const double cube = a1 * a1 * a1;
     double aH, rhoH;
     if (-32.0 * cube - 108.0 * rho2 < 0.0) {                 // single real root
         const double rad = (4.0 / 3.0) * cube + 4.5 * rho2;
         const double s = 0.35355339059327379 * rho + (1.0 / 6.0) * sqrt(rad);   // sqrt(2)/4
-        const double c = cbrt(s);
-        const double zh = c - a1 / (3.0 * c);
+        const double rc = rcbrt(s);                           // 1 / c,  c = s^(1/3) = s * rc^2
+        const double c = s * rc * rc;
+        const double zh = c - a1 * (rc * (1.0 / 3.0));        // c - (a+1)/(3c)
         aH = -(zh * zh);
         rhoH = 1.4142135623730951 * zh;
     } else {                                                  // three real roots
@@ -113,8 +131,6 @@ __device__ __forceinline__ void project_K(double a, double b1, double b2, double
         aH = -0.5 * (zh * zh);
         rhoH = zh;
     }
-    double ct = 1.0, st = 0.0;                                // atan2(0, 0) = 0
-    if (rho > 0.0) { ct = b1 / rho; st = b2 / rho; }
     qa = aH; qb1 = rhoH * ct; qb2 = rhoH * st;
 }
 
@@ -131,32 +147,39 @@ __global__ void __launch_bounds__(kThreads) k_stepB(unsigned int N, const double
 // --------------------------------------------------------------------------- K3
 // gradPhi = grad_st phi (registers only); p = gradPhi + mu/r; q = stepB(p);
 // mu += r (gradPhi - q); mu_rho = max(mu_rho, 0); criterion partial sums with the updated mu.
-__global__ void __launch_bounds__(kThreads) k_prox_dual(Dims d, const double *__restrict__ phi, double *__restrict__ mu,
+// One thread per (y, x) column marching through t with phi(n-1), phi(n), phi(n+1) in registers:
+// phi is read once from HBM (a flat sweep re-reads it three times at HD size).
+__global__ void __launch_bounds__(kThreads, 4) k_prox_dual(Dims d, const double *__restrict__ phi, double *__restrict__ mu,
                                                          double *__restrict__ q, double r, double inv_r,
                                                          double *__restrict__ partials)
 {
     __shared__ double red[64];
     double acc[2] = {0.0, 0.0};
     const unsigned int stride = gridDim.x * blockDim.x;
-    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < d.N; k += stride) {
-        int n, y, x;
-        decode(k, d, n, y, x);
-        const double gt = dw(phi, k, d.P, n, d.Nt);
-        const double gx = dw(phi, k, 1u, x, d.Nx);
-        const double gy = dw(phi, k, (unsigned int)d.Nx, y, d.Ny);
-        const double m0 = mu[k], m1 = mu[d.N + k], m2 = mu[2u * d.N + k];
-        double qa, qb1, qb2;
-        project_K(gt + inv_r * m0, gx + inv_r * m1, gy + inv_r * m2, qa, qb1, qb2);
-        q[k] = qa; q[d.N + k] = qb1; q[2u * d.N + k] = qb2;
-        double rho = m0 + r * (gt - qa);
-        rho = fmax(rho, 0.0);
-        mu[k] = rho;
-        mu[d.N + k] = m1 + r * (gx - qb1);
-        mu[2u * d.N + k] = m2 + r * (gy - qb2);
-        const double g2 = gx * gx + gy * gy;
-        const double res = gt + 0.5 * g2;
-        acc[0] += rho * fabs(res);
-        acc[1] += rho * g2;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.P; i += stride) {
+        const int y = (int)(i / (unsigned int)d.Nx), x = (int)(i - (unsigned int)y * d.Nx);
+        double p_m = 0.0, p_c = phi[i], p_p = phi[d.P + i];
+        for (int n = 0; n < d.Nt; n++) {
+            const unsigned int k = (unsigned int)n * d.P + i;
+            const double gt = n == 0 ? p_p - p_c : (n == d.Nt - 1 ? p_c - p_m : 0.5 * p_p - 0.5 * p_m);
+            const double gx = dw(phi, k, 1u, x, d.Nx);
+            const double gy = dw(phi, k, (unsigned int)d.Nx, y, d.Ny);
+            const double m0 = mu[k], m1 = mu[d.N + k], m2 = mu[2u * d.N + k];
+            p_m = p_c; p_c = p_p;
+            if (n + 2 < d.Nt) p_p = phi[k + 2u * d.P];
+            double qa, qb1, qb2;
+            project_K(gt + inv_r * m0, gx + inv_r * m1, gy + inv_r * m2, qa, qb1, qb2);
+            q[k] = qa; q[d.N + k] = qb1; q[2u * d.N + k] = qb2;
+            double rho = m0 + r * (gt - qa);
+            rho = fmax(rho, 0.0);
+            mu[k] = rho;
+            mu[d.N + k] = m1 + r * (gx - qb1);
+            mu[2u * d.N + k] = m2 + r * (gy - qb2);
+            const double g2 = gx * gx + gy * gy;
+            const double res = gt + 0.5 * g2;
+            acc[0] += rho * fabs(res);
+            acc[1] += rho * g2;
+        }
     }
     block_sum<2>(acc, red);
     if (threadIdx.x == 0) { partials[2 * blockIdx.x] = acc[0]; partials[2 * blockIdx.x + 1] = acc[1]; }
@@ -302,13 +325,13 @@ void launch_init_state(cudaStream_t st, Dims d, const double *rho0, const double
 void launch_rhs(cudaStream_t st, Dims d, const double *mu, const double *q, const double *rho0, const double *rhoT,
                 double r, double *F)
 {
-    k_rhs<<<blocks_for(d.N), kThreads, 0, st>>>(d, mu, q, rho0, rhoT, r, F);
+    k_rhs<<<blocks_for(d.P), kThreads, 0, st>>>(d, mu, q, rho0, rhoT, r, F);
 }
 
 int launch_prox_dual(cudaStream_t st, Dims d, const double *phi, double *mu, double *q, double r, double *partials,
                      int max_blocks)
 {
-    int blocks = blocks_for(d.N, max_blocks);
+    int blocks = blocks_for(d.P, max_blocks);
     k_prox_dual<<<blocks, kThreads, 0, st>>>(d, phi, mu, q, r, 1.0 / r, partials);
     return blocks;
 }
