@@ -31,13 +31,6 @@ struct Coef {            // matrix entries of A, exactly as the reference assemb
     double r;
 };
 
-// diagonal entry of A for a cell with the given boundary flags: -r * L_ii + r*eps
-__device__ __forceinline__ double diag_entry(const Coef &c, bool bt, bool by, bool bx)
-{
-    const double Lii = (bt ? -1.0 : -2.0) + ((bx ? -1.0 : -2.0) + (by ? -1.0 : -2.0));
-    return -c.r * Lii + c.reps;
-}
-
 __global__ void __launch_bounds__(512, 2) cg_stream_kernel(CgArgs a)
 {
     __shared__ double red[128];
@@ -71,26 +64,32 @@ __global__ void __launch_bounds__(512, 2) cg_stream_kernel(CgArgs a)
     for (; it < a.maxiter; it++) {
         if (sqrt(rr) < atol) { info = 0; break; }
         const double beta = it > 0 ? rr / rr_prev : 0.0;
-        // ---- phase A
+        // ---- phase A: one thread per (y, x) column marching through t with p_new(n-1), p_new(n),
+        // p_new(n+1) in registers, so p_old and r cross HBM once per iteration even when a plane is
+        // far larger than L2 keeps between two visits (the four in-plane neighbours are L1/L2 hits)
         acc[0] = 0.0;
-        for (unsigned int k = tid; k < N; k += nth) {
-            const unsigned int row = k / (unsigned int)Nx;
-            const int x = (int)(k - row * (unsigned int)Nx);
-            const unsigned int nn = row / (unsigned int)Ny;
-            const int y = (int)(row - nn * (unsigned int)Ny);
-            const int n = (int)nn;
-            const double pc = pold[k] * beta + a.r[k];
-            double s = 0.0;
-            if (n > 0) s += c.off * (pold[k - P] * beta + a.r[k - P]);
-            if (y > 0) s += c.off * (pold[k - Nx] * beta + a.r[k - Nx]);
-            if (x > 0) s += c.off * (pold[k - 1] * beta + a.r[k - 1]);
-            s += diag_entry(c, n == 0 || n == Nt - 1, y == 0 || y == Ny - 1, x == 0 || x == Nx - 1) * pc;
-            if (x < Nx - 1) s += c.off * (pold[k + 1] * beta + a.r[k + 1]);
-            if (y < Ny - 1) s += c.off * (pold[k + Nx] * beta + a.r[k + Nx]);
-            if (n < Nt - 1) s += c.off * (pold[k + P] * beta + a.r[k + P]);
-            pnew[k] = pc;
-            a.q[k] = s;
-            acc[0] += pc * s;
+        for (unsigned int i = tid; i < P; i += nth) {
+            const int y = (int)(i / (unsigned int)Nx), x = (int)(i - (unsigned int)y * Nx);
+            const bool xl = x > 0, xh = x < Nx - 1, yl = y > 0, yh = y < Ny - 1;
+            const double dxy = (xl && xh ? -2.0 : -1.0) + (yl && yh ? -2.0 : -1.0);
+            double pm = 0.0, pc = pold[i] * beta + a.r[i], pp = pold[P + i] * beta + a.r[P + i];
+            for (int n = 0; n < Nt; n++) {
+                const unsigned int k = (unsigned int)n * P + i;
+                const double Lii = ((n == 0 || n == Nt - 1) ? -1.0 : -2.0) + dxy;
+                double s = 0.0;
+                if (n > 0) s += c.off * pm;
+                if (yl) s += c.off * (pold[k - Nx] * beta + a.r[k - Nx]);
+                if (xl) s += c.off * (pold[k - 1] * beta + a.r[k - 1]);
+                s += (-c.r * Lii + c.reps) * pc;
+                if (xh) s += c.off * (pold[k + 1] * beta + a.r[k + 1]);
+                if (yh) s += c.off * (pold[k + Nx] * beta + a.r[k + Nx]);
+                if (n < Nt - 1) s += c.off * pp;
+                pnew[k] = pc;
+                a.q[k] = s;
+                acc[0] += pc * s;
+                pm = pc; pc = pp;
+                if (n + 2 < Nt) pp = pold[k + 2u * P] * beta + a.r[k + 2u * P];
+            }
         }
         grid_allreduce<1>(a.sync, gen, acc, red);
         if (*a.sync.error) return;

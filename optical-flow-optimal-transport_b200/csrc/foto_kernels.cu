@@ -13,15 +13,6 @@ namespace {
 
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ void decode(unsigned int k, const Dims &d, int &n, int &y, int &x)
-{
-    unsigned int row = k / (unsigned int)d.Nx;
-    x = (int)(k - row * (unsigned int)d.Nx);
-    unsigned int nn = row / (unsigned int)d.Ny;
-    y = (int)(row - nn * (unsigned int)d.Ny);
-    n = (int)nn;
-}
-
 // "weird" central difference with one-sided Neumann rows (operators.py:33-48), unit spacing
 __device__ __forceinline__ double dw(const double *__restrict__ f, unsigned int k, unsigned int st, int i, int n)
 {
