@@ -162,6 +162,13 @@ int  foto_gn_system(const double *f1, const double *f2, int w, int h, double alp
 int  foto_warp_apply(const double *f1, const double *u, const double *v, int w, int h,
                      const double *m_or_null, double *out);
 
+/* Middlebury .flo payload (utils.saveFlo, utils.py:273-292): n = w*h pairs of float32 (u, v),
+ * interleaved; the 12-byte header (float32 202021.25, int32 w, int32 h) is written by the caller. */
+int  foto_pack_flo(const double *u, const double *v, int n, float *out_2n);
+/* utils.EE / utils.AE (utils.py:294-338): out6 = [sum EE, sum EE^2, #EE<=50, sum AE, sum AE^2, #AE not NaN];
+ * mean = sum/count, stddev = sqrt(sumsq/count - mean^2). */
+int  foto_flow_metrics(const double *u, const double *v, const double *uGT, const double *vGT, int n, double *out6);
+
 /* Many independent pairs of one shape, sharded over devices by a work queue (one host thread
  * per device, no collective).  rho0s/rhoTs: n_pairs*P doubles,
  * us/vs/ms: n_pairs*P doubles; n_outer[n_pairs]; device_ids[n_dev] (NULL: devices 0..n_dev-1). */

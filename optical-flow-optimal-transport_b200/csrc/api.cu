@@ -776,6 +776,43 @@ extern "C" int foto_warp_apply(const double *f1, const double *u, const double *
     return FOTO_OK;
 }
 
+extern "C" int foto_pack_flo(const double *u, const double *v, int n, float *out)
+{
+    if (!u || !v || !out || n < 1) { set_error("foto_pack_flo: bad argument"); return FOTO_ERR_ARG; }
+    foto_ctx *c = nullptr;
+    FOTO_TRY(default_ctx(&c));
+    FOTO_TRY(ctx_bind(c));
+    FOTO_TRY(ensure(&c->io, &c->io_bytes, 3 * Carver::bytes(n)));
+    IoPlan io(c);
+    double *du = io.slot(n), *dv = io.slot(n); float *dout = (float *)io.slot(n);
+    FOTO_TRY(h2d(c, du, u, n)); FOTO_TRY(h2d(c, dv, v, n));
+    launch_pack_flo(c->stream, (unsigned int)n, du, dv, dout);
+    c->stats.launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, dout, (size_t)n * 2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FOTO_OK;
+}
+
+extern "C" int foto_flow_metrics(const double *u, const double *v, const double *ug, const double *vg, int n, double *out6)
+{
+    if (!u || !v || !ug || !vg || !out6 || n < 1) { set_error("foto_flow_metrics: bad argument"); return FOTO_ERR_ARG; }
+    foto_ctx *c = nullptr;
+    FOTO_TRY(default_ctx(&c));
+    FOTO_TRY(ctx_bind(c));
+    FOTO_TRY(ensure(&c->io, &c->io_bytes, 4 * Carver::bytes(n) + Carver::bytes(6 * 148 * 8 + 8)));
+    IoPlan io(c);
+    double *d[4] = {io.slot(n), io.slot(n), io.slot(n), io.slot(n)}, *part = io.slot(6 * 148 * 8 + 8);
+    const double *h[4] = {u, v, ug, vg};
+    for (int i = 0; i < 4; i++) FOTO_TRY(h2d(c, d[i], h[i], n));
+    launch_flow_metrics(c->stream, (unsigned int)n, d[0], d[1], d[2], d[3], part, part + 6 * 148 * 8);
+    c->stats.launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    FOTO_TRY(d2h(c, out6, part + 6 * 148 * 8, 6));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FOTO_OK;
+}
+
 // ------------------------------------------------------------------------------- batch driver
 // Pairs are independent: one host thread per device pulls pair indices
 // from an atomic counter (dynamic load balance: iteration counts are data dependent), runs the

@@ -360,3 +360,74 @@ void launch_axis_apply(cudaStream_t st, const double *in, double *out, const dou
 }
 
 }  // namespace foto
+
+// ------------------------------------------------------------------------------- next-tier rows
+// (SURVEY.md section 8f): .flo egress packing and endpoint/angular error metrics on the device.
+namespace foto {
+namespace {
+
+// Middlebury .flo payload: float32 (u, v) interleaved, row-major (utils.py:285-292)
+__global__ void __launch_bounds__(256) k_pack_flo(unsigned int n, const double *__restrict__ u,
+                                                   const double *__restrict__ v, float2 *__restrict__ out)
+{
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+        out[k] = make_float2((float)u[k], (float)v[k]);
+}
+
+// EE = sqrt((u-uGT)^2 + (v-vGT)^2), kept when EE <= 50 (utils.py:308-312);
+// AE = acos((1 + u uGT + v vGT) / (sqrt(1+u^2+v^2) sqrt(1+uGT^2+vGT^2))), kept when not NaN (utils.py:331-335).
+// out6 = [sum EE, sum EE^2, count EE, sum AE, sum AE^2, count AE]
+__global__ void __launch_bounds__(256) k_flow_metrics(unsigned int n, const double *__restrict__ u, const double *__restrict__ v,
+                                                       const double *__restrict__ ug, const double *__restrict__ vg,
+                                                       double *__restrict__ partials)
+{
+    __shared__ double red[32 * 4];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0}, cnt[2] = {0.0, 0.0};
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const double du = u[k] - ug[k], dv = v[k] - vg[k];
+        const double ee = sqrt(du * du + dv * dv);
+        if (ee <= 50.0) { acc[0] += ee; acc[1] += ee * ee; cnt[0] += 1.0; }
+        const double ae = acos((1.0 + u[k] * ug[k] + v[k] * vg[k]) /
+                               (sqrt(1.0 + u[k] * u[k] + v[k] * v[k]) * sqrt(1.0 + ug[k] * ug[k] + vg[k] * vg[k])));
+        if (ae == ae) { acc[2] += ae; acc[3] += ae * ae; cnt[1] += 1.0; }
+    }
+    block_sum<4>(acc, red);
+    block_sum<2>(cnt, red);
+    if (threadIdx.x == 0) {
+        double *p = partials + 6 * blockIdx.x;
+        p[0] = acc[0]; p[1] = acc[1]; p[2] = cnt[0]; p[3] = acc[2]; p[4] = acc[3]; p[5] = cnt[1];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sum6(const double *__restrict__ partials, int blocks, double *__restrict__ out6)
+{
+    __shared__ double red[32 * 4];
+    double a[4] = {0, 0, 0, 0}, b[2] = {0, 0};
+    for (int i = threadIdx.x; i < blocks; i += blockDim.x) {
+        const double *p = partials + 6 * i;
+        a[0] += p[0]; a[1] += p[1]; b[0] += p[2]; a[2] += p[3]; a[3] += p[4]; b[1] += p[5];
+    }
+    block_sum<4>(a, red);
+    block_sum<2>(b, red);
+    if (threadIdx.x == 0) { out6[0] = a[0]; out6[1] = a[1]; out6[2] = b[0]; out6[3] = a[2]; out6[4] = a[3]; out6[5] = b[1]; }
+}
+
+}  // namespace
+
+void launch_pack_flo(cudaStream_t st, unsigned int n, const double *u, const double *v, float *out)
+{
+    k_pack_flo<<<blocks_for(n), 256, 0, st>>>(n, u, v, (float2 *)out);
+}
+
+// partials: 6 * 1184 doubles
+void launch_flow_metrics(cudaStream_t st, unsigned int n, const double *u, const double *v, const double *ug,
+                         const double *vg, double *partials, double *out6)
+{
+    const int blocks = blocks_for(n, 148 * 8);
+    k_flow_metrics<<<blocks, 256, 0, st>>>(n, u, v, ug, vg, partials);
+    k_sum6<<<1, 256, 0, st>>>(partials, blocks, out6);
+}
+
+}  // namespace foto

@@ -28,6 +28,10 @@ void launch_flow(cudaStream_t st, Dims d, const double *phi, double *u, double *
 // K7: utils.apply_opticalflow (utils.py:186-248); g = scratch P doubles
 void launch_warp(cudaStream_t st, int w, int h, const double *f1, const double *u, const double *v,
                  const double *m_or_null, double *g, double *out);
+// next-tier rows: .flo payload packing, EE/AE metric sums
+void launch_pack_flo(cudaStream_t st, unsigned int n, const double *u, const double *v, float *out);
+void launch_flow_metrics(cudaStream_t st, unsigned int n, const double *u, const double *v, const double *ug,
+                         const double *vg, double *partials, double *out6);
 // generic tridiagonal-along-one-axis apply used by foto_op_apply
 void launch_axis_apply(cudaStream_t st, const double *in, double *out, const double *lo, const double *di,
                        const double *up, int transpose, unsigned int stride, int len, unsigned int total,

@@ -25,7 +25,7 @@ EXPORTS = [
     "foto_solve_dev", "foto_gn_solve_dev", "foto_solve_host", "foto_gn_solve_host",
     "foto_solve", "foto_stepB", "foto_stepA", "foto_rhs", "foto_flow_from_phi", "foto_op_apply",
     "foto_tri_coeffs", "foto_gn_solve", "foto_gn_system", "foto_warp_apply",
-    "foto_solve_batch", "foto_gn_solve_batch",
+    "foto_solve_batch", "foto_gn_solve_batch", "foto_pack_flo", "foto_flow_metrics",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -221,6 +221,33 @@ def warp_apply(f1, u, v, w, h, m=None):
         m = _a(m, P); mp = _p(m)
     _check(lib().foto_warp_apply(_p(f1), _p(u), _p(v), int(w), int(h), mp, _p(out)))
     return out
+
+
+def pack_flo(u, v):
+    """float32 interleaved (u, v) payload of a Middlebury .flo file, packed on the GPU."""
+    u = _a(u); v = _a(v, u.size)
+    out = np.empty(2 * u.size, dtype=np.float32)
+    _check(lib().foto_pack_flo(_p(u), _p(v), int(u.size), out.ctypes.data_as(C.POINTER(C.c_float))))
+    return out
+
+
+def save_flo(w, h, u, v, pathname):
+    """utils.saveFlo (utils.py:273-292) with the payload packed on the GPU; byte-identical files."""
+    payload = pack_flo(u, v)
+    with open(pathname, "wb") as f:
+        np.array([202021.25], dtype=np.float32).tofile(f)
+        np.array([w, h], dtype=np.int32).tofile(f)
+        payload.tofile(f)
+
+
+def flow_metrics(u, v, uGT, vGT):
+    """(AEE, SDEE, AAE, SDAE) as utils.EE / utils.AE compute them (EE <= 50 and non-NaN AE filters)."""
+    u = _a(u); n = u.size
+    out = np.empty(6)
+    _check(lib().foto_flow_metrics(_p(u), _p(_a(v, n)), _p(_a(uGT, n)), _p(_a(vGT, n)), int(n), _p(out)))
+    aee = out[0] / out[2]; aae = out[3] / out[5]
+    sdee = np.sqrt(max(out[1] / out[2] - aee * aee, 0.0)); sdae = np.sqrt(max(out[4] / out[5] - aae * aae, 0.0))
+    return aee, sdee, aae, sdae
 
 
 def _devices(devices):

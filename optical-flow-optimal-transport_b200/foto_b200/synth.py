@@ -60,6 +60,15 @@ def perturb_brightness(f, h, w, seed):
     return _quantise(img).ravel()
 
 
+def normalize_pair(f0, f1):
+    """Joint mass / peak normalisation of the reference's bin/normalize_image.py:20-26: each frame is
+    scaled to unit mass, then both are divided by the larger peak and re-quantised to 8 bits."""
+    a = np.asarray(f0, dtype=np.float64) / np.sum(f0)
+    b = np.asarray(f1, dtype=np.float64) / np.sum(f1)
+    scale = max(a.max(), b.max())
+    return _quantise(a / scale), _quantise(b / scale)
+
+
 def two_squares(n=32):
     """The reference author's commented-out fixture (main.py:55-65): two shifted unit
     squares on an n x n grid.  Exercises the 'inside K' branch of the projection."""

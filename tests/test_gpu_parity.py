@@ -382,3 +382,51 @@ def test_dct_exact_full_size_matches_tight_cg():
     # and stays within the 1e-6 px endpoint-error contract of the as-shipped reference
     sub = g["sub"]
     assert epe_max(u[sub], v[sub], g["u"], g["v"]) < 1e-6
+
+
+# ----------------------------------------------------------------------------- next-tier rows
+def test_flo_egress_byte_identical(tmp_path, monkeypatch):
+    monkeypatch.syspath_prepend(os.path.join(PKG, "shim"))
+    sys.modules.pop("utils", None)
+    import utils
+    rng = np.random.default_rng(5)
+    w, h = 37, 23
+    u, v = rng.standard_normal(w * h) * 3, rng.standard_normal(w * h) * 3
+    utils.saveFlo(w, h, u, v, str(tmp_path / "ref.flo"))          # numpy astype(float32), as the reference does
+    foto_b200.save_flo(w, h, u, v, str(tmp_path / "gpu.flo"))
+    assert open(tmp_path / "ref.flo", "rb").read() == open(tmp_path / "gpu.flo", "rb").read()
+    sys.modules.pop("utils", None)
+
+
+def test_flow_metrics_match_numpy(monkeypatch):
+    monkeypatch.syspath_prepend(os.path.join(PKG, "shim"))
+    sys.modules.pop("utils", None)
+    import utils
+    rng = np.random.default_rng(6)
+    n = 388 * 584
+    u, v = rng.standard_normal(n), rng.standard_normal(n)
+    ug, vg = u + 0.1 * rng.standard_normal(n), v + 0.1 * rng.standard_normal(n)
+    ug[::1000] += 100.0                                           # EE > 50: filtered out
+    aee, sdee, aae, sdae = foto_b200.flow_metrics(u, v, ug, vg)
+    r_aee, r_sdee = utils.EE(584, 388, u, v, ug, vg)
+    r_aae, r_sdae = utils.AE(584, 388, u, v, ug, vg)
+    assert abs(aee - r_aee) < 1e-12 and abs(sdee - r_sdee) < 1e-9
+    assert abs(aae - r_aae) < 1e-12 and abs(sdae - r_sdae) < 1e-9
+    sys.modules.pop("utils", None)
+
+
+def test_stepA_large_grid_streaming_property():
+    """A grid too large for the on-chip CG variant (2 M cells): the streaming kernel must return a phi
+    that satisfies scipy's stopping rule, whatever variant the default context prefers."""
+    rng = np.random.default_rng(8)
+    Nt, Ny, Nx = 4, 540, 960
+    N = Nt * Ny * Nx
+    mu = rng.standard_normal(3 * N); q = rng.standard_normal(3 * N)
+    rho0 = rng.random(Ny * Nx); rhoT = rng.random(Ny * Nx)
+    F = foto_b200.rhs(mu, q, rho0, rhoT, 1.0, Nt, Nx, Ny)
+    phi, iters, info = foto_b200.stepA(mu, q, rho0, rhoT, 1.0, 1e-3, Nt, Nx, Ny)
+    assert info == 0 and 50 < iters < 1000
+    L = foto_b200.op_apply("laplacian_st", "N", Nt, Nx, Ny, 1, 1, 1, phi)
+    assert np.linalg.norm((-L + 1e-3 * phi) - F) < 1.0001e-6 * np.linalg.norm(F)
+    phi_d, _, _ = foto_b200.stepA(mu, q, rho0, rhoT, 1.0, 1e-3, Nt, Nx, Ny, backend=foto_b200.POISSON_DCT_EXACT)
+    assert np.linalg.norm((-foto_b200.op_apply("laplacian_st", "N", Nt, Nx, Ny, 1, 1, 1, phi_d) + 1e-3 * phi_d) - F) < 1e-11 * np.linalg.norm(F)
