@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_onchip_kernel(CgArgs a, Onchip
     auto nothing = [] {};
 
     const double bb = grid_sum(acc, true, nothing);
-    int it = 0, status = a.maxiter;
+    int it = 0, status = bb == 0.0 ? 0 : a.maxiter;      // scipy: "if bnrm2 == 0: return b, 0"
     if (!abort && bb != 0.0) {
         const double atol = a.rtol * sqrt(bb);
         double rr = bb, rr_prev = 0.0;

@@ -430,3 +430,37 @@ def test_stepA_large_grid_streaming_property():
     assert np.linalg.norm((-L + 1e-3 * phi) - F) < 1.0001e-6 * np.linalg.norm(F)
     phi_d, _, _ = foto_b200.stepA(mu, q, rho0, rhoT, 1.0, 1e-3, Nt, Nx, Ny, backend=foto_b200.POISSON_DCT_EXACT)
     assert np.linalg.norm((-foto_b200.op_apply("laplacian_st", "N", Nt, Nx, Ny, 1, 1, 1, phi_d) + 1e-3 * phi_d) - F) < 1e-11 * np.linalg.norm(F)
+
+
+def test_identical_frames_zero_rhs(oracle):
+    """rho0 == rhoT: the right-hand side is pure rounding noise of the time interpolation (1e-17), CG
+    converges on it, the flow is exactly zero and the loop stops after one outer iteration."""
+    h, w, Nt = 30, 44, 4
+    f0, _ = synth.make_pair(h, w, seed=3)
+    u, v, m, info = foto_b200.solve(f0, f0, Nt, w, h, r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=20)
+    uo, vo, mo, io = oracle.solve(f0, f0, Nt, w, h, r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=20, return_info=True)
+    assert info["n_outer"] == io["n_outer"] == 1
+    assert list(info["cg_iters"]) == list(io["cg_iters"]) and list(info["cg_info"]) == [0]
+    assert not u.any() and not v.any() and not m.any() and not uo.any()
+    # an exactly zero right-hand side: scipy returns b (= 0) with info 0 and no iteration
+    z = np.zeros(3 * Nt * h * w)
+    phi, iters, cinfo = foto_b200.stepA(z, z, np.zeros(h * w), np.zeros(h * w), 1.0, 1e-3, Nt, w, h)
+    assert iters == 0 and cinfo == 0 and not phi.any()
+
+
+def test_cg_maxiter_warning_path(capsys, monkeypatch):
+    """A tiny eps makes the 1000-iteration budget bind: info = maxiter, the shim prints the
+    reference's WARNING (benamou_brenier.py:86-87) and carries on."""
+    monkeypatch.syspath_prepend(os.path.join(PKG, "shim"))
+    for name in ("operators", "utils", "benamou_brenier", "classical"):
+        sys.modules.pop(name, None)
+    import benamou_brenier as bb
+    h, w, Nt = 128, 192, 4
+    f0, f1 = synth.make_pair(h, w, seed=4)
+    u, v, m, info = foto_b200.solve(f0, f1, Nt, w, h, r=1.0, convergence_tol=0.1, reg_epsilon=1e-12, max_it=2)
+    assert list(info["cg_info"]) == [1000, 1000] and list(info["cg_iters"]) == [1000, 1000]
+    bb.solve(f0, f1, Nt, w, h, r=1.0, convergence_tol=0.1, reg_epsilon=1e-12, max_it=1)
+    out = capsys.readouterr().out
+    assert "WARNING: CG did not converge in 1000 iterations." in out
+    for name in ("operators", "utils", "benamou_brenier", "classical"):
+        sys.modules.pop(name, None)
