@@ -329,12 +329,39 @@ def run_b200(args):
                     "foto_dct_exact_note": "opt-in exact Poisson back-end; differs from the reference's truncated CG by "
                                            "~5e-7 relative (parity-gated against the tight oracle only)"},
         }
+        if world == 1 and not args.no_hd:
+            line["roofline_streaming_hd"] = hd_roofline(ctx, torch, dev, peak)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single()
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def hd_roofline(ctx, torch, dev, peak):
+    """HBM-bound evidence: one outer ALG2 iteration on a 1080x1920x16 grid (3.2 GB working set, 25x the
+    L2), streaming CG kernel, CUDA events per kernel.  Not part of `value`."""
+    from foto_b200 import synth
+    h, w, Nt = 1080, 1920, 16
+    P_, N_ = h * w, 16 * h * w
+    f0, f1 = synth.make_pair(h, w, seed=0)
+    a = torch.from_numpy(f0).to(dev); b = torch.from_numpy(f1).to(dev)
+    o = [torch.empty(P_, dtype=torch.float64, device=dev) for _ in range(3)]
+    kw = dict(r=1.0, convergence_tol=0.0, reg_epsilon=1e-3, max_it=1)
+    ctx.solve_dev(a.data_ptr(), b.data_ptr(), Nt, w, h, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), **kw)
+    ctx.set_profiling(True); ctx.reset_stats()
+    ctx.solve_dev(a.data_ptr(), b.data_ptr(), Nt, w, h, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), **kw)
+    st = ctx.stats(); ctx.set_profiling(False)
+    gbs = lambda bytes_per_cell, cells, ms: bytes_per_cell * cells / max(ms, 1e-9) / 1e6
+    k1 = gbs(RHS_BYTES_PER_CELL, st["rhs_cells"], st["rhs_ms"])
+    k2 = gbs(CG_BYTES_PER_CELL_ITER, st["cg_cells"], st["cg_ms"])
+    k3 = gbs(PROX_BYTES_PER_CELL, st["prox_cells"], st["prox_ms"])
+    return {"grid": [Nt, h, w], "cells": N_, "working_set_GB": 12 * N_ * 8 / 1e9, "peak": peak, "unit": "GB/s",
+            "K1_rhs": {"achieved": k1, "frac": k1 / peak, "ms": st["rhs_ms"]},
+            "K2a_cg_stream": {"achieved": k2, "frac": k2 / peak, "us_per_cg_iteration": 1e3 * st["cg_ms"] / max(st["cg_iterations"], 1),
+                              "cg_iterations": st["cg_iterations"], "bytes_per_cell_iteration": CG_BYTES_PER_CELL_ITER},
+            "K3_prox_dual": {"achieved": k3, "frac": k3 / peak, "ms": st["prox_ms"]}}
 
 
 def main():
@@ -346,6 +373,7 @@ def main():
     ap.add_argument("--pairs-per-gpu", type=int, default=4)
     ap.add_argument("--cg-variant", type=int, default=None, help="-1 auto, 0 streaming, 1 on-chip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hd", action="store_true", help="skip the 1080x1920x16 streaming-roofline measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
