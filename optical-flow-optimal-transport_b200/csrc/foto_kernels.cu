@@ -138,26 +138,37 @@ __global__ void __launch_bounds__(kThreads) k_stepB(unsigned int N, const double
 // --------------------------------------------------------------------------- K3
 // gradPhi = grad_st phi (registers only); p = gradPhi + mu/r; q = stepB(p);
 // mu += r (gradPhi - q); mu_rho = max(mu_rho, 0); criterion partial sums with the updated mu.
-// One thread per (y, x) column marching through t with phi(n-1), phi(n), phi(n+1) in registers:
-// phi is read once from HBM (a flat sweep re-reads it three times at HD size).
-__global__ void __launch_bounds__(kThreads, 4) k_prox_dual(Dims d, const double *__restrict__ phi, double *__restrict__ mu,
+// Threads march through t with phi(n-1), phi(n), phi(n+1) in registers: phi is read once from HBM
+// (a flat sweep re-reads it three times at HD size).
+constexpr int kTChunk = 1 << 20;    // one chunk: splitting t across threads (4 planes each) measured slower at 1080x1920x16
+__global__ void __launch_bounds__(kThreads, 3) k_prox_dual(Dims d, const double *__restrict__ phi, double *__restrict__ mu,
                                                          double *__restrict__ q, double r, double inv_r,
                                                          double *__restrict__ partials)
 {
     __shared__ double red[64];
     double acc[2] = {0.0, 0.0};
     const unsigned int stride = gridDim.x * blockDim.x;
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.P; i += stride) {
+    // work item = (chunk of kTChunk time planes, column): marching keeps phi(n-1), phi(n), phi(n+1) in
+    // registers (one extra phi word per chunk end), chunking keeps enough threads in flight when Nt is large
+    const unsigned int nchunk = ((unsigned int)d.Nt + kTChunk - 1) / kTChunk, items = nchunk * d.P;
+    for (unsigned int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += stride) {
+        const unsigned int chunk = it / d.P, i = it - chunk * d.P;
         const int y = (int)(i / (unsigned int)d.Nx), x = (int)(i - (unsigned int)y * d.Nx);
-        double p_m = 0.0, p_c = phi[i], p_p = phi[d.P + i];
-        for (int n = 0; n < d.Nt; n++) {
+        const int nb = (int)(chunk * kTChunk), ne = min(nb + kTChunk, d.Nt);
+        const unsigned int kb = (unsigned int)nb * d.P + i;
+        double p_m = nb > 0 ? phi[kb - d.P] : 0.0, p_c = phi[kb], p_p = nb + 1 < d.Nt ? phi[kb + d.P] : 0.0;
+        // software pipeline: the three mu words of plane n+1 are requested before the projection of
+        // plane n is computed (the kernel is latency-bound: 4 HBM words per cell and iteration in flight)
+        double n0 = mu[kb], n1 = mu[d.N + kb], n2 = mu[2u * d.N + kb];
+        for (int n = nb; n < ne; n++) {
             const unsigned int k = (unsigned int)n * d.P + i;
             const double gt = n == 0 ? p_p - p_c : (n == d.Nt - 1 ? p_c - p_m : 0.5 * p_p - 0.5 * p_m);
             const double gx = dw(phi, k, 1u, x, d.Nx);
             const double gy = dw(phi, k, (unsigned int)d.Nx, y, d.Ny);
-            const double m0 = mu[k], m1 = mu[d.N + k], m2 = mu[2u * d.N + k];
+            const double m0 = n0, m1 = n1, m2 = n2;
             p_m = p_c; p_c = p_p;
             if (n + 2 < d.Nt) p_p = phi[k + 2u * d.P];
+            if (n + 1 < ne) { n0 = mu[k + d.P]; n1 = mu[d.N + k + d.P]; n2 = mu[2u * d.N + k + d.P]; }
             double qa, qb1, qb2;
             project_K(gt + inv_r * m0, gx + inv_r * m1, gy + inv_r * m2, qa, qb1, qb2);
             q[k] = qa; q[d.N + k] = qb1; q[2u * d.N + k] = qb2;

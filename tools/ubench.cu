@@ -124,6 +124,19 @@ __global__ void k_allreduce(unsigned long long *slots, unsigned int *counter, in
     if (tid == 0 && cta == 0) { *cycles = clock64() - t0; *out = total; }
 }
 
+// pure streaming with R read streams and W write streams of n doubles each (what K3 does: R=4, W=6)
+template <int R, int W> __global__ void __launch_bounds__(256) k_stream(const double *__restrict__ in, double *__restrict__ out, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; r++) s += in[r * n + k];
+#pragma unroll
+        for (int w = 0; w < W; w++) out[w * n + k] = s + w;
+    }
+}
+
 __global__ void k_fill(unsigned long long *p, int n, unsigned long long v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
 int main()
@@ -198,6 +211,19 @@ int main()
                    (mode & 16) ? "counter+partials" : "root gather", mode & 1, (mode >> 1) & 1, (mode >> 2) & 1, (mode & 8) ? "sc" : "acq_rel",
                    (double)h / iters, cudaGetErrorString(e), r);
         }
+    }
+    {
+        const size_t n = 33177600;     // 1080 x 1920 x 16
+        double *in, *o; cudaMalloc(&in, n * 8 * 8); cudaMalloc(&o, n * 8 * 8);
+        cudaMemset(in, 0, n * 8 * 8);
+        auto run = [&](auto kern, int R, int W, const char *name) {
+            for (int rep = 0; rep < 3; rep++) { cudaEventRecord(e0); kern<<<148 * 16, 256>>>(in, o, n); cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1); }
+            printf("stream %s: %d read + %d write streams of 265 MB: %.3f ms = %.0f GB/s\n", name, R, W, ms, (R + W) * n * 8 / ms / 1e6);
+        };
+        run(k_stream<1, 1>, 1, 1, "copy");
+        run(k_stream<4, 6>, 4, 6, "K3-like");
+        run(k_stream<6, 1>, 6, 1, "K1-like");
+        run(k_stream<6, 4>, 6, 4, "CG-like");
     }
     printf("last error: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
