@@ -113,14 +113,15 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------ CPU oracle legs
-def _cpu_sample_worker(seed):
-    """One bounded CPU sample: the first CPU_SAMPLE_OUTER outer iterations of one pair."""
+def _cpu_sample_worker(arg):
+    """One bounded CPU sample: the first n_outer outer iterations of one pair."""
+    seed, n_outer = arg if isinstance(arg, tuple) else (arg, CPU_SAMPLE_OUTER)
     import oracle
     from foto_b200 import synth
     f0, f1 = synth.make_pair(H, W, seed=pair_seed(0, seed))
     t0 = time.perf_counter()
     kw = dict(PARAMS)
-    kw["max_it"] = CPU_SAMPLE_OUTER
+    kw["max_it"] = n_outer
     kw["convergence_tol"] = 0.0
     _, _, _, info = oracle.solve(f0, f1, NT, W, H, return_info=True, **kw)
     return time.perf_counter() - t0, int(info["n_outer"])
@@ -145,19 +146,20 @@ def run_reference(args):
     import multiprocessing as mp
     import oracle
     oracle.build()
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = min(avail, 64)           # the path is DRAM-bound on the host: more processes only add contention
     times = []
     with mp.get_context("fork").Pool(cores) as pool:
         for step in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            res = pool.map(_cpu_sample_worker, range(cores))
+            res = pool.map(_cpu_sample_worker, [(i, 1) for i in range(cores)])   # 1 of ~9 outer iterations each
             dt = time.perf_counter() - t0
             if step >= args.warmup:
                 times.append(dt)
             outer = res[0][1]
     total = sum(times)
     value = args.steps * cores * (outer / EXPECTED_OUTER) / total
-    sample = (f"per step, {cores} processes each run the first {outer} of {EXPECTED_OUTER} outer iterations of one "
+    sample = (f"per step, {cores} processes (of {avail} usable cores) each run the first {outer} of {EXPECTED_OUTER} outer iterations of one "
               f"388x584 pair with the C oracle (port of the reference's algorithm; the reference itself is pure "
               f"Python and cannot travel to the GPU box); pairs/s scaled by {EXPECTED_OUTER}/{outer}")
     line = {"impl": "reference", "metric": "FOTO frame-pairs/s at 388x584", "value": value, "unit": "pairs/s",
@@ -288,10 +290,12 @@ def run_b200(args):
         cg_bytes = CG_BYTES_PER_CELL_ITER * stats["cg_cells"]
         cg_s = stats["cg_ms"] / 1e3
         achieved = cg_bytes / cg_s / 1e9 if cg_s > 0 else 0.0
-        traffic = None
+        traffic, traffic_src = None, None            # DRAM bytes per launch from the committed ncu --set full capture
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("cg_onchip_kernel" if stats["cg_variant"] == 1 else "cg_stream_kernel")
+            t = json.load(open(tpath)).get("cg_onchip_kernel" if stats["cg_variant"] == 1 else "cg_stream_kernel")
+            if t:
+                traffic, traffic_src = t["dram_bytes_per_launch"], t["source"]
         per_launch_iters = stats["cg_iterations"] / max(stats["cg_launches"], 1)
         line = {
             "metric": "FOTO frame-pairs/s at 388x584", "value": value, "unit": "pairs/s",
@@ -312,7 +316,7 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": {"kernel": "cg_onchip_kernel" if stats["cg_variant"] == 1 else "cg_stream_kernel",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": CG_BYTES_PER_CELL_ITER * N * per_launch_iters,
                          "avg_launch_ms": stats["cg_ms"] / max(stats["cg_launches"], 1),
                          "cg_iterations_per_launch": per_launch_iters,
