@@ -367,6 +367,9 @@ const Config kConfigs[] = {
     {512, 14, (const void *)cg_onchip_kernel<512, 14, true>, (const void *)cg_onchip_kernel<512, 14, false>},
     {1024, 7, (const void *)cg_onchip_kernel<1024, 7, true>, (const void *)cg_onchip_kernel<1024, 7, false>},
     {256, 28, (const void *)cg_onchip_kernel<256, 28, true>, (const void *)cg_onchip_kernel<256, 28, false>},
+    // larger per-SM capacity (9 216 / 10 240 cells) for grids such as 480x640x4 that the first three cannot hold
+    {512, 18, (const void *)cg_onchip_kernel<512, 18, true>, (const void *)cg_onchip_kernel<512, 18, false>},
+    {256, 40, (const void *)cg_onchip_kernel<256, 40, true>, (const void *)cg_onchip_kernel<256, 40, false>},
 };
 constexpr int kNumConfigs = sizeof(kConfigs) / sizeof(kConfigs[0]);
 
