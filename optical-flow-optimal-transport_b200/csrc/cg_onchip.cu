@@ -14,8 +14,10 @@
 //   * synchronises the grid with a two-hop reduction: every CTA publishes its partial dot
 //     product with one release store; one warp of CTA 0 gathers the partials, sums them in a
 //     fixed order and publishes the total; one thread per CTA polls that single word.  Only
-//     148 + 32 threads poll L2 (an all-to-all poll of 148 x 148 threads serialises on the ten
-//     hot cache lines and cost 8 k cycles per barrier), and every CTA reads the same total.
+//     148 + 32 threads poll L2 and every CTA reads the same total.  Measured alternatives, all
+//     slower (profiles/README.md): all-to-all polling of one slot array (148 x 148 threads on ten
+//     hot L2 lines, 8 k cycles per barrier), 16 replicated slot arrays polled by 9 CTAs each
+//     (one hop, but 9.6 instead of 8.9 us per iteration), one private total word per CTA.
 // The kernel is instruction-issue and shared-memory bound, so the per-cell code is branch-free:
 // out-of-domain neighbours are zero cells (subtracting +0.0 is exact, the csr_matvec running
 // sum is unchanged), unused cell slots point at a dead cell and their q is masked to zero.
@@ -139,6 +141,7 @@ constexpr int kTShift = 16, kTMask = 0x3F;
 constexpr int kCntShift = 22;
 constexpr int kEdgeN = 1 << 24, kEdgeS = 1 << 25, kEdgeW = 1 << 26, kEdgeE = 1 << 27, kEdgeAny = 0xF << 24;
 constexpr int kValid = 1 << 28;
+constexpr int kHaloPerThread = 4;      // halo cells per thread the plan guarantees (nhalo <= 4 * threads)
 
 template <int NTHREADS, int CPT, bool UNIT>
 __global__ void __launch_bounds__(NTHREADS, 1) cg_onchip_kernel(CgArgs a, OnchipGeom g)
@@ -169,6 +172,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_onchip_kernel(CgArgs a, Onchip
     // export pointers: N/S edges are indexed [t*tx + lx], W/E edges by the (t, y) row j*RPP + r0
     double *const pN = my_edges + lx, *const pS = my_edges + edge_stride + lx;
     double *const pW = my_edges + 2 * edge_stride + r0, *const pE = my_edges + 3 * edge_stride + r0;
+    const double dg_interior = -a.rcoef * (-6.0) + a.rcoef * a.eps * 1.0;
     double rj[CPT], qj[CPT];        // p lives in shared memory: the register file cannot hold a third vector
     int info[CPT];
 
@@ -264,19 +268,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_onchip_kernel(CgArgs a, Onchip
         double rr = bb, rr_prev = 0.0;
         if (prof) tmark = clock64();
         for (; it < a.maxiter; it++) {
-            if (sqrt(rr) < atol) { status = 0; break; }
             const double beta = it > 0 ? rr / rr_prev : 0.0;
-            // ---- A1: advance the halo copy of p with the neighbours' freshly published r
-            for (int h = tid; h < nhalo; h += NTHREADS) {
-                const double v = __ldcg(g.edges + hsrc[h]);
-                const int i = hdst[h];
-                ps[i] = ps[i] * beta + v;
+            // ---- A1 (first half): request the neighbours' freshly published r (L2 round trip ~700 cycles)
+            // before touching own cells; halo tables hold at most kHaloPerThread entries per thread
+            double hv[kHaloPerThread];
+#pragma unroll
+            for (int e = 0; e < kHaloPerThread; e++) {
+                const int h = tid + e * NTHREADS;
+                hv[e] = h < nhalo ? __ldcg(g.edges + hsrc[h]) : 0.0;
             }
+            // scipy's stopping test "||r|| < atol" (top of the loop).  p may already be advanced when we
+            // leave: only x is returned.  Placed here so that the sqrt overlaps the loads above.
+            if (sqrt(rr) < atol) { status = 0; break; }
             // ---- A2: own cells  p = p*beta + r
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
                 const int si = fresh(info[j]) & kSiMask;
                 ps[si] = ps[si] * beta + rj[j];
+            }
+            // ---- A1 (second half): advance the halo copy of p
+#pragma unroll
+            for (int e = 0; e < kHaloPerThread; e++) {
+                const int h = tid + e * NTHREADS;
+                if (h < nhalo) { const int i = hdst[h]; ps[i] = ps[i] * beta + hv[e]; }
             }
             __syncthreads();
             lap(0);
@@ -286,7 +300,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_onchip_kernel(CgArgs a, Onchip
             for (int j = 0; j < CPT; j++) {
                 const int inf = fresh(info[j]);
                 const double *pc = ps + (inf & kSiMask);
-                const double dg = dtab[(inf >> kCntShift) & 3];
+                const int code = (inf >> kCntShift) & 3;
+                double dg = dg_interior;                 // 6 neighbours: no shared-memory lookup
+                if (code != 3) dg = dtab[code];
                 const double c = pc[0];
                 double s = 0.0;
                 if (UNIT) {                           // r == 1: products with -1.0 are exact negations
@@ -421,6 +437,7 @@ Plan make_plan(OnchipScratch &d, int device, int Nt, int Ny, int Nx)
                 const size_t smem = ((((size_t)(Nt + 2) * (ty + 2) * (tx + 2) + 1) & ~size_t(1)) + (size_t)CPT * T + 64 + 4) * 8
                                   + (size_t)4 * Nt * (tx + ty) * sizeof(int);
                 if (smem > d.smem_optin) continue;
+                if (2LL * Nt * (tx + ty) > (long long)kHaloPerThread * T) continue;
                 // work per SM ~ passes * threads (issue slots); then prefer wide tiles: a warp that
                 // spans several tile rows takes the W/E edge-export path in every cell and has
                 // shared-memory bank conflicts at the row breaks; then short halos
