@@ -507,3 +507,29 @@ def test_solve_and_gn_odd_shapes_vs_oracle(oracle, Nt, Ny, Nx):
     gu, gv, gm, gi = foto_b200.gn_solve(f0, f1, Nx, Ny, 0.1, 0.2)
     ou, ov, om = oracle.gn_solve(f0, f1, Nx, Ny, 0.1, 0.2)
     assert relerr(gu, ou) < 1e-9 and relerr(gv, ov) < 1e-9 and relerr(gm, om) < 1e-9
+
+
+def test_deterministic_bitwise_repeat():
+    """Fixed-order reductions everywhere (no floating-point atomics): two runs give identical bits."""
+    h, w, Nt = 97, 146, 4
+    f0, f1 = synth.make_pair(h, w, seed=0)
+    kw = dict(r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=3)
+    a = foto_b200.solve(f0, f1, Nt, w, h, **kw)
+    b = foto_b200.solve(f0, f1, Nt, w, h, **kw)
+    for x, y in zip(a[:3], b[:3]):
+        np.testing.assert_array_equal(x, y)
+    ga = foto_b200.gn_solve(f0, f1, w, h, 0.1, 0.2); gb = foto_b200.gn_solve(f0, f1, w, h, 0.1, 0.2)
+    np.testing.assert_array_equal(ga[0], gb[0])
+
+
+def test_run_sh_parameters_nt16_on_chip(oracle):
+    """The author's production parameters (run.sh:114): Nt=16, eps=1e-2, tol=0.01, on a half-resolution
+    frame; 16 time planes per tile in the on-chip CG kernel."""
+    h, w, Nt = 97, 146, 16
+    f0, f1 = synth.make_pair(h, w, seed=0)
+    kw = dict(r=1.0, convergence_tol=0.01, reg_epsilon=1e-2, max_it=6)
+    u, v, m, info = foto_b200.solve(f0, f1, Nt, w, h, **kw)
+    uo, vo, mo, io = oracle.solve(f0, f1, Nt, w, h, return_info=True, **kw)
+    assert info["n_outer"] == io["n_outer"] == 6
+    np.testing.assert_array_equal(info["cg_iters"], io["cg_iters"])
+    assert relerr(u, uo) < 1e-9 and relerr(v, vo) < 1e-9 and relerr(m, mo) < 1e-9
