@@ -129,6 +129,30 @@ int  foto_gn_solve_host(foto_ctx *ctx, const double *f1, const double *f2, int w
                         double alpha, double lambda, double rtol, int max_it,
                         double *u, double *v, double *m, int *iters, int *info);
 
+/* ---- time-slab building blocks (device pointers) -----------------------------------
+ * One huge volume split into contiguous time slabs, one per rank: rank owns the global planes
+ * [n0, n0 + nloc) of gNt.  The exchange steps (1-plane halos of mu_rho, q_a and phi, the t <-> y
+ * all-to-all of the DCT, the all-reduce of the two criterion sums) are collectives issued by the host
+ * driver (foto_b200/slab.py over torch.distributed / NCCL); these are the compute steps in between.
+ * Pointers address the first OWNED plane; 3-component fields have component stride cs (doubles);
+ * halo planes at -1 and nloc must be addressable where they exist globally. */
+/* launch on the caller's stream (NULL = legacy default stream), or back on the context's own stream */
+int  foto_ctx_set_stream(foto_ctx *ctx, void *cuda_stream, int use_own_stream);
+/* K1 on a slab: solve_benamou_brenier_step's right-hand side, benamou_brenier.py:64-82 */
+int  foto_slab_rhs_dev(foto_ctx *ctx, const double *d_mu, const double *d_q, unsigned long long cs,
+                       const double *d_rho0, const double *d_rhoT, double r, int gNt, int n0, int nloc,
+                       int Nx, int Ny, double *d_F);
+/* K3 on a slab: stepB + stepC + criterion sums (benamou_brenier.py:213-251); d_out2 = [num, den] of this slab */
+int  foto_slab_prox_dev(foto_ctx *ctx, const double *d_phi, double *d_mu, double *d_q, unsigned long long cs,
+                        double r, int gNt, int n0, int nloc, int Nx, int Ny, double *d_out2);
+/* K2b pieces: x/y DCT of nplanes planes (inverse != 0: DCT-III); t solve on a [gNt][ny_loc][Nx] block of rows y_off.. */
+int  foto_dct_xy_dev(foto_ctx *ctx, const double *d_in, double *d_out, double *d_tmp, int nplanes, int gNt,
+                     int Ny, int Nx, int inverse);
+int  foto_dct_t_solve_dev(foto_ctx *ctx, const double *d_in, double *d_out, int gNt, int Ny, int Nx, int y_off,
+                          int ny_loc, double r, double eps);
+/* K4 on device buffers: utils.opticalflow_from_benamoubrenier, utils.py:148 */
+int  foto_flow_dev(foto_ctx *ctx, const double *d_phi, int Nt, int Nx, int Ny, double *d_u, double *d_v, double *d_m);
+
 /* ---- host-buffer API (what the reference's Python modules bind) ------------------- */
 /* benamou_brenier.solve, benamou_brenier.py:151 */
 int  foto_solve(const double *rho0, const double *rhoT, int Nt, int Nx, int Ny,

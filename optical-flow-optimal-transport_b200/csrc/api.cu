@@ -38,7 +38,8 @@ enum Cat { CAT_RHS = 0, CAT_CG, CAT_PROX, CAT_FLOW, CAT_GN, CAT_COUNT };
 struct foto_ctx {
     int device = 0;
     int num_sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;          // stream every kernel of the context is launched on
+    cudaStream_t own_stream = nullptr;      // created with the context; `stream` may be redirected (foto_ctx_set_stream)
     char *ws = nullptr;     size_t ws_bytes = 0;      // solver workspace
     char *io = nullptr;     size_t io_bytes = 0;      // staging for the host-buffer API
     unsigned int *sync_counter = nullptr;
@@ -149,7 +150,8 @@ extern "C" int foto_ctx_create(int device, foto_ctx **out)
     c->num_sms = prop.multiProcessorCount;
     int rc = [&]() -> int {
         CUDA_TRY(cudaSetDevice(device));
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        c->stream = c->own_stream;
         CUDA_TRY(cudaMalloc((void **)&c->sync_counter, 256));
         CUDA_TRY(cudaMalloc((void **)&c->sync_partials, sizeof(double) * 2 * kMaxVals * kMaxBlocks));
         CUDA_TRY(cudaMalloc((void **)&c->prox_partials, sizeof(double) * 2 * kProxMaxBlocks));
@@ -171,6 +173,7 @@ extern "C" void foto_ctx_destroy(foto_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    c->stream = c->own_stream;
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (auto e : c->watch) if (e) cudaEventDestroy(e);
     cudaFree(c->ws); cudaFree(c->io); cudaFree(c->sync_counter); cudaFree(c->sync_partials);
@@ -240,6 +243,7 @@ static int make_dims(int Nt, int Nx, int Ny, Dims *d)
     unsigned long long P = (unsigned long long)Nx * Ny, N = P * Nt;
     if (3ull * N >= (1ull << 32)) { set_error("grid too large for 32-bit cell indices (3N = %llu)", 3ull * N); return FOTO_ERR_ARG; }
     d->Nt = Nt; d->Ny = Ny; d->Nx = Nx; d->P = (unsigned int)P; d->N = (unsigned int)N;
+    d->n0 = 0; d->gNt = Nt; d->cs = (unsigned int)N;
     return FOTO_OK;
 }
 
@@ -810,6 +814,96 @@ extern "C" int foto_flow_metrics(const double *u, const double *v, const double 
     CUDA_TRY(cudaGetLastError());
     FOTO_TRY(d2h(c, out6, part + 6 * 148 * 8, 6));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FOTO_OK;
+}
+
+// ------------------------------------------------------------------------------- time-slab building blocks
+// One huge volume split into contiguous time slabs, one per rank (second row).  The
+// exchange steps (1-plane halos, the t <-> y all-to-all of the DCT, the 2-scalar all-reduce of the criterion)
+// are NCCL calls made by the host driver (foto_b200/slab.py, torch.distributed); these entry points are the
+// compute between them.  Arrays are device pointers to the first OWNED plane; 3-component fields have
+// component stride cs (in doubles) and addressable halo planes at -1 and nloc where those exist globally.
+extern "C" int foto_ctx_set_stream(foto_ctx *c, void *stream, int use_own_stream)
+{
+    if (!c) return FOTO_ERR_ARG;
+    FOTO_TRY(ctx_bind(c));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->stream = use_own_stream ? c->own_stream : (cudaStream_t)stream;     // NULL = the legacy default stream
+    return FOTO_OK;
+}
+
+static int slab_dims(int gNt, int n0, int nloc, int Nx, int Ny, unsigned long long cs, Dims *d)
+{
+    if (gNt < 2 || nloc < 1 || n0 < 0 || n0 + nloc > gNt || Nx < 2 || Ny < 2) { set_error("bad slab geometry"); return FOTO_ERR_ARG; }
+    const unsigned long long P = (unsigned long long)Nx * Ny;
+    if (cs < P * nloc || 3ull * cs >= (1ull << 32)) { set_error("bad slab component stride"); return FOTO_ERR_ARG; }
+    d->Nt = nloc; d->Ny = Ny; d->Nx = Nx; d->P = (unsigned int)P; d->N = (unsigned int)(P * nloc);
+    d->n0 = n0; d->gNt = gNt; d->cs = (unsigned int)cs;
+    return FOTO_OK;
+}
+
+extern "C" int foto_slab_rhs_dev(foto_ctx *c, const double *mu, const double *q, unsigned long long cs, const double *rho0,
+                                 const double *rhoT, double r, int gNt, int n0, int nloc, int Nx, int Ny, double *F)
+{
+    if (!c || !mu || !q || !rho0 || !rhoT || !F) { set_error("foto_slab_rhs_dev: NULL argument"); return FOTO_ERR_ARG; }
+    Dims d;
+    FOTO_TRY(slab_dims(gNt, n0, nloc, Nx, Ny, cs, &d));
+    FOTO_TRY(ctx_bind(c));
+    launch_rhs(c->stream, d, mu, q, rho0, rhoT, r, F);
+    c->stats.launches++;
+    CUDA_TRY(cudaGetLastError());
+    return FOTO_OK;
+}
+
+extern "C" int foto_slab_prox_dev(foto_ctx *c, const double *phi, double *mu, double *q, unsigned long long cs, double r,
+                                  int gNt, int n0, int nloc, int Nx, int Ny, double *d_out2)
+{
+    if (!c || !phi || !mu || !q || !d_out2) { set_error("foto_slab_prox_dev: NULL argument"); return FOTO_ERR_ARG; }
+    Dims d;
+    FOTO_TRY(slab_dims(gNt, n0, nloc, Nx, Ny, cs, &d));
+    FOTO_TRY(ctx_bind(c));
+    const int blocks = launch_prox_dual(c->stream, d, phi, mu, q, r, c->prox_partials, kProxMaxBlocks);
+    launch_crit_final(c->stream, c->prox_partials, blocks, d_out2);
+    c->stats.launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return FOTO_OK;
+}
+
+extern "C" int foto_dct_xy_dev(foto_ctx *c, const double *in, double *out, double *tmp, int nplanes, int gNt, int Ny, int Nx,
+                               int inverse)
+{
+    if (!c || !in || !out || !tmp || nplanes < 1) { set_error("foto_dct_xy_dev: bad argument"); return FOTO_ERR_ARG; }
+    Dims d;
+    FOTO_TRY(make_dims(gNt, Nx, Ny, &d));
+    FOTO_TRY(ctx_bind(c));
+    FOTO_TRY(ensure_dct_tables(c, d));
+    FOTO_TRY(launch_dct_xy(c->stream, c->dct, nplanes, Ny, Nx, in, out, tmp, inverse));
+    c->stats.launches += 2;
+    return FOTO_OK;
+}
+
+extern "C" int foto_dct_t_solve_dev(foto_ctx *c, const double *in, double *out, int gNt, int Ny, int Nx, int y_off, int ny_loc,
+                                    double r, double eps)
+{
+    if (!c || !in || !out || y_off < 0 || ny_loc < 1 || y_off + ny_loc > Ny) { set_error("foto_dct_t_solve_dev: bad argument"); return FOTO_ERR_ARG; }
+    Dims d;
+    FOTO_TRY(make_dims(gNt, Nx, Ny, &d));
+    FOTO_TRY(ctx_bind(c));
+    FOTO_TRY(ensure_dct_tables(c, d));
+    FOTO_TRY(launch_dct_t_solve(c->stream, c->dct, gNt, ny_loc, Nx, y_off, r, eps, in, out));
+    c->stats.launches++;
+    return FOTO_OK;
+}
+
+extern "C" int foto_flow_dev(foto_ctx *c, const double *d_phi, int Nt, int Nx, int Ny, double *d_u, double *d_v, double *d_m)
+{
+    if (!c || !d_phi || !d_u || !d_v || !d_m) { set_error("foto_flow_dev: NULL argument"); return FOTO_ERR_ARG; }
+    Dims d;
+    FOTO_TRY(make_dims(Nt, Nx, Ny, &d));
+    FOTO_TRY(ctx_bind(c));
+    launch_flow(c->stream, d, d_phi, d_u, d_v, d_m);
+    c->stats.launches += 2;
+    CUDA_TRY(cudaGetLastError());
     return FOTO_OK;
 }
 

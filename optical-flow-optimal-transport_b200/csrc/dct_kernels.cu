@@ -182,27 +182,55 @@ static void gemm(cudaStream_t st, int M, int N, int K, const double *A, int lda,
     k_dgemm_nn<<<grid, GT, 0, st>>>(M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC);
 }
 
-// phi = A^-1 F.  tabs: device tables for this grid; w0, w1: two N-double scratch volumes.
+static int t_solve(cudaStream_t st, const DctTables &tb, int Nt, int Ny, int Nx, const double *lam_y, double r, double eps,
+                   const double *in, double *out)
+{
+    const int blocks = (int)(((long long)Ny * Nx + 255) / 256);
+#define FOTO_T_SOLVE(M) k_t_solve<M><<<blocks, 256, 0, st>>>(Nt, Ny, Nx, r, eps, tb.Ct, tb.lam_t, lam_y, tb.lam_x, in, out)
+    if (Nt <= 4) FOTO_T_SOLVE(4);
+    else if (Nt <= 8) FOTO_T_SOLVE(8);
+    else if (Nt <= 16) FOTO_T_SOLVE(16);
+    else if (Nt <= 32) FOTO_T_SOLVE(32);
+    else if (Nt <= 64) FOTO_T_SOLVE(64);
+    else { set_error("dct_exact supports Nt <= 64"); return FOTO_ERR_ARG; }
+#undef FOTO_T_SOLVE
+    return FOTO_OK;
+}
+
+// x and y transforms of `nplanes` planes (forward: DCT-II, inverse: DCT-III); tmp: nplanes*Ny*Nx doubles
+int launch_dct_xy(cudaStream_t st, const DctTables &tb, int nplanes, int Ny, int Nx, const double *in, double *out,
+                  double *tmp, int inverse)
+{
+    const long long P = (long long)Ny * Nx;
+    if (!inverse) {
+        gemm(st, nplanes * Ny, Nx, Nx, in, Nx, 0, tb.CxT, Nx, 0, tmp, Nx, 0, 1);       // rows * Cx^T
+        gemm(st, Ny, Nx, Ny, tb.Cy, Ny, 0, tmp, Nx, P, out, Nx, P, nplanes);            // Cy * plane
+    } else {
+        gemm(st, Ny, Nx, Ny, tb.CyT, Ny, 0, in, Nx, P, tmp, Nx, P, nplanes);
+        gemm(st, nplanes * Ny, Nx, Nx, tmp, Nx, 0, tb.Cx, Nx, 0, out, Nx, 0, 1);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return FOTO_OK;
+}
+
+// t transform, division by the eigenvalues and inverse t transform on a [Nt][ny_loc][Nx] block whose rows
+// are the global rows y_off .. y_off + ny_loc - 1 (time-slab mode after the all-to-all transpose)
+int launch_dct_t_solve(cudaStream_t st, const DctTables &tb, int Nt, int ny_loc, int Nx, int y_off, double r, double eps,
+                       const double *in, double *out)
+{
+    FOTO_TRY(t_solve(st, tb, Nt, ny_loc, Nx, tb.lam_y + y_off, r, eps, in, out));
+    CUDA_TRY(cudaGetLastError());
+    return FOTO_OK;
+}
+
+// phi = A^-1 F.  tb: device tables for this grid; w0, w1: two N-double scratch volumes.
 // 5 launches: x, y forward transforms; fused t-transform / divide / inverse t; y, x inverse transforms.
 int launch_poisson_dct(cudaStream_t st, const DctTables &tb, int Nt, int Ny, int Nx, double r, double eps,
                        const double *F, double *phi, double *w0, double *w1)
 {
-    const long long P = (long long)Ny * Nx;
-    // forward: rows * Cx^T  (M = Nt*Ny, K = Nx),   Cy * plane (batched over t),   Ct * [Nt x P]
-    gemm(st, Nt * Ny, Nx, Nx, F, Nx, 0, tb.CxT, Nx, 0, w0, Nx, 0, 1);
-    gemm(st, Ny, Nx, Ny, tb.Cy, Ny, 0, w0, Nx, P, w1, Nx, P, Nt);
-    {
-        const int blocks = (int)((P + 255) / 256);
-        if (Nt <= 4) k_t_solve<4><<<blocks, 256, 0, st>>>(Nt, Ny, Nx, r, eps, tb.Ct, tb.lam_t, tb.lam_y, tb.lam_x, w1, w0);
-        else if (Nt <= 8) k_t_solve<8><<<blocks, 256, 0, st>>>(Nt, Ny, Nx, r, eps, tb.Ct, tb.lam_t, tb.lam_y, tb.lam_x, w1, w0);
-        else if (Nt <= 16) k_t_solve<16><<<blocks, 256, 0, st>>>(Nt, Ny, Nx, r, eps, tb.Ct, tb.lam_t, tb.lam_y, tb.lam_x, w1, w0);
-        else if (Nt <= 32) k_t_solve<32><<<blocks, 256, 0, st>>>(Nt, Ny, Nx, r, eps, tb.Ct, tb.lam_t, tb.lam_y, tb.lam_x, w1, w0);
-        else if (Nt <= 64) k_t_solve<64><<<blocks, 256, 0, st>>>(Nt, Ny, Nx, r, eps, tb.Ct, tb.lam_t, tb.lam_y, tb.lam_x, w1, w0);
-        else { set_error("dct_exact supports Nt <= 64"); return FOTO_ERR_ARG; }
-    }
-    // inverse (DCT-III = transpose)
-    gemm(st, Ny, Nx, Ny, tb.CyT, Ny, 0, w0, Nx, P, w1, Nx, P, Nt);
-    gemm(st, Nt * Ny, Nx, Nx, w1, Nx, 0, tb.Cx, Nx, 0, phi, Nx, 0, 1);
+    FOTO_TRY(launch_dct_xy(st, tb, Nt, Ny, Nx, F, w1, w0, 0));
+    FOTO_TRY(t_solve(st, tb, Nt, Ny, Nx, tb.lam_y, r, eps, w1, w0));
+    FOTO_TRY(launch_dct_xy(st, tb, Nt, Ny, Nx, w0, phi, w1, 1));
     CUDA_TRY(cudaGetLastError());
     return FOTO_OK;
 }

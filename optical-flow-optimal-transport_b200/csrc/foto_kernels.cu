@@ -33,11 +33,11 @@ __global__ void __launch_bounds__(kThreads) k_init_state(Dims d, const double *_
         double w2 = (double)n / (double)(d.Nt - 1);
         double w1 = 1.0 - w2;
         mu[k] = w1 * rho0[i] + w2 * rhoT[i];
-        mu[d.N + k] = 0.0;
-        mu[2u * d.N + k] = 0.0;
+        mu[d.cs + k] = 0.0;
+        mu[2u * d.cs + k] = 0.0;
         q[k] = 0.0;
-        q[d.N + k] = 0.0;
-        q[2u * d.N + k] = 0.0;
+        q[d.cs + k] = 0.0;
+        q[2u * d.cs + k] = 0.0;
     }
 }
 
@@ -66,23 +66,26 @@ __global__ void __launch_bounds__(kThreads, 8) k_rhs(Dims d, const double *__res
                                                    double r, double *__restrict__ F)
 {
     const unsigned int stride = gridDim.x * blockDim.x;
-    const double *mu1 = mu + d.N, *q1 = q + d.N, *mu2 = mu + 2u * d.N, *q2 = q + 2u * d.N;
+    const double *mu1 = mu + d.cs, *q1 = q + d.cs, *mu2 = mu + 2u * d.cs, *q2 = q + 2u * d.cs;
+    auto has = [&](int nl) { const int gn = d.n0 + nl; return gn >= 0 && gn < d.gNt; };   // plane exists globally
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.P; i += stride) {
         const int y = (int)(i / (unsigned int)d.Nx), x = (int)(i - (unsigned int)y * d.Nx);
-        double w_m = 0.0, w_c = wv(mu, q, r, i), w_p = wv(mu, q, r, d.P + i);
+        double w_m = has(-1) ? mu[(long long)i - (long long)d.P] - r * q[(long long)i - (long long)d.P] : 0.0;
+        double w_c = wv(mu, q, r, i), w_p = has(1) ? wv(mu, q, r, d.P + i) : 0.0;
         for (int n = 0; n < d.Nt; n++) {
             const unsigned int k = (unsigned int)n * d.P + i;
+            const int gn = d.n0 + n;
             double s = 0.0;
-            if (n == 0) { s += -1.0 * w_c; s += 1.0 * w_p; }
-            else if (n == d.Nt - 1) { s += -1.0 * w_m; s += 1.0 * w_c; }
+            if (gn == 0) { s += -1.0 * w_c; s += 1.0 * w_p; }
+            else if (gn == d.gNt - 1) { s += -1.0 * w_m; s += 1.0 * w_c; }
             else { s += -0.5 * w_m; s += 0.5 * w_p; }
             s = dw_acc(s, mu1, q1, r, k, 1u, x, d.Nx);
             s = dw_acc(s, mu2, q2, r, k, (unsigned int)d.Nx, y, d.Ny);
-            if (n == 0) s -= (rho0[i] - mu[k] + r * q[k]);
-            if (n == d.Nt - 1) s += (rhoT[i] - mu[k] + r * q[k]);
+            if (gn == 0) s -= (rho0[i] - mu[k] + r * q[k]);
+            if (gn == d.gNt - 1) s += (rhoT[i] - mu[k] + r * q[k]);
             F[k] = s;
             w_m = w_c; w_c = w_p;
-            if (n + 2 < d.Nt) w_p = wv(mu, q, r, k + 2u * d.P);
+            if (has(n + 2)) w_p = wv(mu, q, r, k + 2u * d.P);
         }
     }
 }
@@ -156,27 +159,29 @@ __global__ void __launch_bounds__(kThreads, 3) k_prox_dual(Dims d, const double 
         const int y = (int)(i / (unsigned int)d.Nx), x = (int)(i - (unsigned int)y * d.Nx);
         const int nb = (int)(chunk * kTChunk), ne = min(nb + kTChunk, d.Nt);
         const unsigned int kb = (unsigned int)nb * d.P + i;
-        double p_m = nb > 0 ? phi[kb - d.P] : 0.0, p_c = phi[kb], p_p = nb + 1 < d.Nt ? phi[kb + d.P] : 0.0;
+        auto has = [&](int nl) { const int gn = d.n0 + nl; return gn >= 0 && gn < d.gNt; };   // plane exists globally
+        double p_m = has(nb - 1) ? phi[(long long)kb - (long long)d.P] : 0.0, p_c = phi[kb], p_p = has(nb + 1) ? phi[kb + d.P] : 0.0;
         // software pipeline: the three mu words of plane n+1 are requested before the projection of
         // plane n is computed (the kernel is latency-bound: 4 HBM words per cell and iteration in flight)
-        double n0 = mu[kb], n1 = mu[d.N + kb], n2 = mu[2u * d.N + kb];
+        double n0 = mu[kb], n1 = mu[d.cs + kb], n2 = mu[2u * d.cs + kb];
         for (int n = nb; n < ne; n++) {
             const unsigned int k = (unsigned int)n * d.P + i;
-            const double gt = n == 0 ? p_p - p_c : (n == d.Nt - 1 ? p_c - p_m : 0.5 * p_p - 0.5 * p_m);
+            const int gn = d.n0 + n;
+            const double gt = gn == 0 ? p_p - p_c : (gn == d.gNt - 1 ? p_c - p_m : 0.5 * p_p - 0.5 * p_m);
             const double gx = dw(phi, k, 1u, x, d.Nx);
             const double gy = dw(phi, k, (unsigned int)d.Nx, y, d.Ny);
             const double m0 = n0, m1 = n1, m2 = n2;
             p_m = p_c; p_c = p_p;
-            if (n + 2 < d.Nt) p_p = phi[k + 2u * d.P];
-            if (n + 1 < ne) { n0 = mu[k + d.P]; n1 = mu[d.N + k + d.P]; n2 = mu[2u * d.N + k + d.P]; }
+            if (has(n + 2)) p_p = phi[k + 2u * d.P];
+            if (n + 1 < ne) { n0 = mu[k + d.P]; n1 = mu[d.cs + k + d.P]; n2 = mu[2u * d.cs + k + d.P]; }
             double qa, qb1, qb2;
             project_K(gt + inv_r * m0, gx + inv_r * m1, gy + inv_r * m2, qa, qb1, qb2);
-            q[k] = qa; q[d.N + k] = qb1; q[2u * d.N + k] = qb2;
+            q[k] = qa; q[d.cs + k] = qb1; q[2u * d.cs + k] = qb2;
             double rho = m0 + r * (gt - qa);
             rho = fmax(rho, 0.0);
             mu[k] = rho;
-            mu[d.N + k] = m1 + r * (gx - qb1);
-            mu[2u * d.N + k] = m2 + r * (gy - qb2);
+            mu[d.cs + k] = m1 + r * (gx - qb1);
+            mu[2u * d.cs + k] = m2 + r * (gy - qb2);
             const double g2 = gx * gx + gy * gy;
             const double res = gt + 0.5 * g2;
             acc[0] += rho * fabs(res);

@@ -5,9 +5,14 @@
 namespace foto {
 
 struct Dims {
-    int Nt, Ny, Nx;
+    int Nt, Ny, Nx;     // Nt = time planes held locally
     unsigned int P;     // Nx*Ny
     unsigned int N;     // Nt*P   (grids up to 2^31-1 cells)
+    // time-slab view (foto_slab_*): this rank owns the global planes [n0, n0 + Nt) of gNt; 3-component
+    // fields have component stride cs, and planes -1 and Nt (halos) are addressable when they exist
+    // globally.  Whole-volume calls use n0 = 0, gNt = Nt, cs = N.
+    int n0, gNt;
+    unsigned int cs;
 };
 
 // ---- FOTO pointwise / stencil kernels (foto_kernels.cu) --------------------------------
@@ -78,6 +83,10 @@ struct DctTables {              // device pointers, owned by the context, valid 
 void dct_host_tables(int n, std::vector<double> &C, std::vector<double> &Ct, std::vector<double> &lam);
 int launch_poisson_dct(cudaStream_t st, const DctTables &tb, int Nt, int Ny, int Nx, double r, double eps,
                        const double *F, double *phi, double *w0, double *w1);
+int launch_dct_xy(cudaStream_t st, const DctTables &tb, int nplanes, int Ny, int Nx, const double *in, double *out,
+                  double *tmp, int inverse);
+int launch_dct_t_solve(cudaStream_t st, const DctTables &tb, int Nt, int ny_loc, int Nx, int y_off, double r, double eps,
+                       const double *in, double *out);
 
 // ---- Gennert-Negahdaripour (gn_kernels.cu) ---------------------------------------------
 // K5: fx, fy (central, zero on the border), ft, Jacobi inverse diagonal, right-hand side

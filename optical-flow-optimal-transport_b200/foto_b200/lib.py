@@ -26,6 +26,8 @@ EXPORTS = [
     "foto_solve", "foto_stepB", "foto_stepA", "foto_rhs", "foto_flow_from_phi", "foto_op_apply",
     "foto_tri_coeffs", "foto_gn_solve", "foto_gn_system", "foto_warp_apply",
     "foto_solve_batch", "foto_gn_solve_batch", "foto_pack_flo", "foto_flow_metrics",
+    "foto_ctx_set_stream", "foto_slab_rhs_dev", "foto_slab_prox_dev", "foto_dct_xy_dev", "foto_dct_t_solve_dev",
+    "foto_flow_dev",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -325,6 +327,36 @@ class Context:
         out = (C.c_longlong * (8 * 1024))()
         _check(lib().foto_debug_onchip_prof(self._h, int(bool(enable)), out))
         return np.array(out, dtype=np.int64).reshape(1024, 8)
+
+    # ---- time-slab building blocks (raw device pointers; see foto_b200/slab.py) ----------
+    def set_stream(self, cuda_stream=None):
+        """Launch on the given CUDA stream handle (0 = legacy default stream); None: the context's own stream."""
+        own = cuda_stream is None
+        _check(lib().foto_ctx_set_stream(self._h, C.c_void_p(0 if own else int(cuda_stream)), int(own)))
+
+    def slab_rhs(self, d_mu, d_q, cs, d_rho0, d_rhoT, r, gNt, n0, nloc, Nx, Ny, d_F):
+        vp = C.c_void_p
+        _check(lib().foto_slab_rhs_dev(self._h, vp(d_mu), vp(d_q), C.c_ulonglong(cs), vp(d_rho0), vp(d_rhoT), _d(r),
+                                       int(gNt), int(n0), int(nloc), int(Nx), int(Ny), vp(d_F)))
+
+    def slab_prox(self, d_phi, d_mu, d_q, cs, r, gNt, n0, nloc, Nx, Ny, d_out2):
+        vp = C.c_void_p
+        _check(lib().foto_slab_prox_dev(self._h, vp(d_phi), vp(d_mu), vp(d_q), C.c_ulonglong(cs), _d(r), int(gNt), int(n0),
+                                        int(nloc), int(Nx), int(Ny), vp(d_out2)))
+
+    def dct_xy(self, d_in, d_out, d_tmp, nplanes, gNt, Ny, Nx, inverse):
+        vp = C.c_void_p
+        _check(lib().foto_dct_xy_dev(self._h, vp(d_in), vp(d_out), vp(d_tmp), int(nplanes), int(gNt), int(Ny), int(Nx),
+                                     int(bool(inverse))))
+
+    def dct_t_solve(self, d_in, d_out, gNt, Ny, Nx, y_off, ny_loc, r, eps):
+        vp = C.c_void_p
+        _check(lib().foto_dct_t_solve_dev(self._h, vp(d_in), vp(d_out), int(gNt), int(Ny), int(Nx), int(y_off), int(ny_loc),
+                                          _d(r), _d(eps)))
+
+    def flow_dev(self, d_phi, Nt, Nx, Ny, d_u, d_v, d_m):
+        vp = C.c_void_p
+        _check(lib().foto_flow_dev(self._h, vp(d_phi), int(Nt), int(Nx), int(Ny), vp(d_u), vp(d_v), vp(d_m)))
 
     def event_record(self, which):
         _check(lib().foto_ctx_event_record(self._h, int(which)))

@@ -533,3 +533,35 @@ def test_run_sh_parameters_nt16_on_chip(oracle):
     assert info["n_outer"] == io["n_outer"] == 6
     np.testing.assert_array_equal(info["cg_iters"], io["cg_iters"])
     assert relerr(u, uo) < 1e-9 and relerr(v, vo) < 1e-9 and relerr(m, mo) < 1e-9
+
+
+# ----------------------------------------------------------------------------- time-slab mode (config 5)
+def test_slab_single_rank_equals_whole_volume():
+    """world = 1: the slab driver (halo-aware K1/K3, split DCT pieces, torch stream) must reproduce the
+    whole-volume dct_exact solve bit for bit."""
+    import torch
+    from foto_b200 import slab
+    h, w, Nt = 48, 64, 5
+    f0, f1 = synth.make_pair(h, w, seed=2)
+    dev = torch.device("cuda", 0)
+    kw = dict(r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=6)
+    s = slab.SlabSolver(Nt, w, h, device=dev)
+    u, v, m, info = s.solve(torch.from_numpy(f0).to(dev), torch.from_numpy(f1).to(dev), **kw)
+    uo, vo, mo, io = foto_b200.solve(f0, f1, Nt, w, h, backend=foto_b200.POISSON_DCT_EXACT, **kw)
+    assert info["n_outer"] == io["n_outer"]
+    np.testing.assert_array_equal(u.cpu().numpy(), uo)
+    np.testing.assert_array_equal(m.cpu().numpy(), mo)
+
+
+@pytest.mark.skipif(foto_b200.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("ranks,h,w,Nt", [(2, 48, 64, 5), (2, 61, 83, 4)])
+def test_slab_two_ranks_bit_identical(ranks, h, w, Nt):
+    import subprocess
+    from conftest import ROOT
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ranks}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tools", "run_slab.py"), str(h), str(w), str(Nt), "6", "--check"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    import json
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["bit_identical"] and res["outer"] == res["single_gpu_outer"]

@@ -53,3 +53,15 @@ def test_single_process_identity():
     assert shard.max_over_ranks([3.0]) == [3.0]
     out = shard.gather_rows(np.ones((2, 4)), [0, 1], 2, 4)
     assert out.shape == (2, 4)
+
+
+def test_slab_plan_partitions():
+    from foto_b200 import slab
+    g = slab.plan(64, 2160, 8)
+    assert g["t"][0] == (0, 8) and g["t"][-1] == (56, 64) and sum(b - a for a, b in g["t"]) == 64
+    assert sum(b - a for a, b in g["y"]) == 2160 and all(b > a for a, b in g["y"])
+    g = slab.plan(5, 7, 3)                                  # uneven
+    assert [b - a for a, b in g["t"]] == [1, 2, 2] and [b - a for a, b in g["y"]] == [2, 2, 3]
+    import pytest
+    with pytest.raises(ValueError):
+        slab.plan(2, 100, 4)
