@@ -407,7 +407,10 @@ extern "C" int foto_gn_solve_dev(foto_ctx *c, const double *d_f1, const double *
     a.out = &c->d_res->cg_iters;
     launch_gn_coeffs(c->stream, w, h, d_f1, d_f2, alpha, lambda, fx, fy, dinv, b);
     prof_begin(c, CAT_GN);
-    FOTO_TRY(launch_gn_pcg(c->stream, a, c->gn_grid, c->gn_block));
+    const bool gn_fits = gn_onchip_fits(c->onchip, c->device, h, w);
+    if (c->cg_variant == 1 && !gn_fits) { set_error("image %dx%d does not fit the on-chip GN variant", h, w); return FOTO_ERR_ARG; }
+    if (gn_fits && c->cg_variant != 0) { FOTO_TRY(launch_gn_onchip(c->stream, a, c->device, c->onchip)); c->stats.launches++; }
+    else FOTO_TRY(launch_gn_pcg(c->stream, a, c->gn_grid, c->gn_block));
     prof_end(c);
     c->stats.launches += 2; c->stats.gn_launches++;
     CUDA_TRY(cudaMemcpyAsync(d_u, a.x, P * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));

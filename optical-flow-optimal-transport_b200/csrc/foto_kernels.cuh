@@ -68,6 +68,9 @@ struct OnchipScratch {          // owned by the context
     long long *prof = nullptr;  // 8 cycle counters (debugging aid, see foto_debug_onchip_prof)
     bool attr_set = false;
     int forced_cfg = -1;        // FOTO_ONCHIP_CONFIG: pin one (threads, cells/thread) configuration
+    double *gn_edges = nullptr; size_t gn_edges_bytes = 0;      // gn_onchip.cu
+    unsigned long long *gn_slots = nullptr;
+    bool gn_attr_set = false;
 };
 bool cg_onchip_fits(OnchipScratch &s, int device, int Nt, int Ny, int Nx);
 int launch_cg_onchip(cudaStream_t st, const CgArgs &a, int device, OnchipScratch &s);
@@ -105,5 +108,8 @@ struct GnArgs {
 };
 int gn_pcg_config(int device, int *grid, int *block);
 int launch_gn_pcg(cudaStream_t st, const GnArgs &a, int grid, int block);
+// on-chip resident variant (gn_onchip.cu): uses fx, fy, f2, dinv, b, x, out, sync.error of GnArgs only
+bool gn_onchip_fits(OnchipScratch &s, int device, int h, int w);
+int launch_gn_onchip(cudaStream_t st, const GnArgs &a, int device, OnchipScratch &s);
 
 }  // namespace foto

@@ -565,3 +565,39 @@ def test_slab_two_ranks_bit_identical(ranks, h, w, Nt):
     import json
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert res["bit_identical"] and res["outer"] == res["single_gpu_outer"]
+
+
+def test_gn_large_image_streaming_property():
+    """720x1280 does not fit the on-chip GN kernel: auto must take the streaming kernel and return a
+    solution of A x = b (residual checked with the library's own K5/K6 operator, which the goldens pin);
+    forcing the on-chip kernel must fail loudly, not fall back."""
+    h, w = 720, 1280
+    f0, f1 = synth.make_pair(h, w, seed=12)
+    u, v, m, info = foto_b200.gn_solve(f0, f1, w, h, 0.1, 0.2, rtol=1e-10)
+    assert info["info"] == 0 and info["iters"] > 100
+    y, b = foto_b200.gn_system(f0, f1, w, h, 0.1, 0.2, np.concatenate([u, v, m]))
+    assert np.linalg.norm(y - b) < 2e-10 * np.linalg.norm(b)
+    ctx = foto_b200.Context(0)
+    ctx.set_cg_variant(1)
+    out = [np.empty(h * w) for _ in range(3)]
+    with pytest.raises(ValueError, match="does not fit"):
+        ctx.gn_solve_host(f0, f1, w, h, 0.1, 0.2, *out)
+    ctx.close()
+
+
+def test_gn_onchip_matches_streaming_many_shapes():
+    """The two PCG kernels run the same recurrence with different summation orders: same iteration count
+    (+-1) and the same solution to 1e-12 over tile shapes that exercise uneven splits and 1-pixel-wide tiles."""
+    ctx = foto_b200.Context(0)
+    for (h, w) in [(2, 2), (3, 5), (17, 149), (149, 17), (64, 64), (150, 600), (388, 584), (431, 571)]:
+        f0, f1 = synth.make_pair(h, w, seed=h * 1000 + w)
+        res = {}
+        for var in (0, -1):
+            ctx.set_cg_variant(var)
+            out = [np.empty(h * w) for _ in range(3)]
+            it = ctx.gn_solve_host(f0, f1, w, h, 0.1, 0.2, *out)
+            res[var] = (it, np.concatenate(out))
+        assert abs(res[0][0] - res[-1][0]) <= 1, (h, w, res[0][0], res[-1][0])
+        scale = np.abs(res[0][1]).max() + 1e-300
+        assert np.abs(res[0][1] - res[-1][1]).max() <= 1e-11 * scale, (h, w)
+    ctx.close()
