@@ -143,9 +143,15 @@ constexpr int kEdgeN = 1 << 24, kEdgeS = 1 << 25, kEdgeW = 1 << 26, kEdgeE = 1 <
 constexpr int kValid = 1 << 28;
 constexpr int kHaloPerThread = 4;      // halo cells per thread the plan guarantees (nhalo <= 4 * threads)
 
-template <int NTHREADS, int CPT, bool UNIT>
+// NT == 0: generic cell ownership, cell slot j of a thread is row j*RPP + r0 of the (t, y) rows of the tile.
+// NT > 0 (requires Nt == NT, CPT == NT*YPT): patch ownership, a thread owns all NT time levels of YPT consecutive
+// tile rows at its column, so the t and inner y neighbours of the stencil come from registers (3.5 shared-memory
+// loads per cell instead of 7; the stencil phase is shared-memory-bandwidth bound).
+template <int NTHREADS, int CPT, bool UNIT, int NT = 0, int YPT = 0>
 __global__ void __launch_bounds__(NTHREADS, 1) cg_onchip_kernel(CgArgs a, OnchipGeom g)
 {
+    constexpr bool PATCH = NT > 0;
+    static_assert(!PATCH || CPT == NT * YPT, "patch ownership: CPT = NT * YPT");
     extern __shared__ double smem[];
     const int tid = threadIdx.x, cta = blockIdx.x, ncta = gridDim.x;
     const int Nt = a.Nt, Ny = a.Ny, Nx = a.Nx;
@@ -204,7 +210,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_onchip_kernel(CgArgs a, Onchip
         if (hasE) nhalo += segWE;
     }
     double acc = 0.0;
-    {
+    // patch ownership: first tile row, number of owned rows, base index of cell (t = 0, jy = 0) in ps
+    const int ly0 = r0 * (PATCH ? YPT : 1);
+    const int nval = (PATCH && r0 < RPP) ? min(YPT, max(ty - ly0, 0)) : 0;
+    const int sb = (PY + ly0 + 1) * PX + lx + 1;
+    const int xmiss = (x0 + lx == 0) + (x0 + lx == Nx - 1);
+    const int jTop = (by == 0 && r0 == 0) ? 0 : -1;            // owned row on the global y = 0 boundary
+    const int jBot = (by == g.gy - 1) ? ty - 1 - ly0 : -1;      //                        y = Ny-1
+    const int jS = hasS ? ty - 1 - ly0 : -1;                    // owned row exported to the southern neighbour
+    const bool expN = hasN && r0 == 0, expW = hasW && lx == 0, expE = hasE && lx == tx - 1;
+    if (PATCH) {
+#pragma unroll
+        for (int j = 0; j < CPT; j++) { rj[j] = 0.0; qj[j] = 0.0; info[j] = 0; xs[j * NTHREADS + tid] = 0.0; }
+#pragma unroll
+        for (int jy = 0; jy < (PATCH ? YPT : 0); jy++) {
+            if (jy < nval) {
+#pragma unroll
+                for (int t = 0; t < NT; t++) {
+                    const int ly = ly0 + jy;
+                    const double v = a.b[((size_t)t * Ny + (y0 + ly)) * Nx + (x0 + lx)];
+                    if (expN && jy == 0) my_edges[0 * edge_stride + t * tx + lx] = v;
+                    if (jy == jS) my_edges[1 * edge_stride + t * tx + lx] = v;
+                    if (expW) my_edges[2 * edge_stride + t * ty + ly] = v;
+                    if (expE) my_edges[3 * edge_stride + t * ty + ly] = v;
+                    rj[t * YPT + jy] = v;
+                    acc = fma(v, v, acc);
+                }
+            }
+        }
+    } else {
         const int rows = Nt * ty;
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
@@ -231,6 +265,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_onchip_kernel(CgArgs a, Onchip
             acc = fma(v, v, acc);
         }
     }
+    // patch ownership: diagonal of a cell with 6 - xmiss (t interior) or 5 - xmiss (t = 0, NT-1) neighbours
+    const double dg_ti = -a.rcoef * (-(double)(6 - xmiss)) + a.rcoef * a.eps * 1.0;
+    const double dg_tb = -a.rcoef * (-(double)(5 - xmiss)) + a.rcoef * a.eps * 1.0;
+    double *const qW = my_edges + 2 * edge_stride + ly0, *const qE = my_edges + 3 * edge_stride + ly0;
     unsigned int gen = 0;
     bool abort = false;
     long long tmark = 0;
@@ -281,10 +319,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_onchip_kernel(CgArgs a, Onchip
             // leave: only x is returned.  Placed here so that the sqrt overlaps the loads above.
             if (sqrt(rr) < atol) { status = 0; break; }
             // ---- A2: own cells  p = p*beta + r
+            if (PATCH) {
 #pragma unroll
-            for (int j = 0; j < CPT; j++) {
-                const int si = fresh(info[j]) & kSiMask;
-                ps[si] = ps[si] * beta + rj[j];
+                for (int jy = 0; jy < (PATCH ? YPT : 0); jy++) {
+                    if (jy < nval) {
+#pragma unroll
+                        for (int t = 0; t < NT; t++) {
+                            const int si = fresh(sb) + t * plane + jy * PX;
+                            ps[si] = ps[si] * beta + rj[t * YPT + jy];
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < CPT; j++) {
+                    const int si = fresh(info[j]) & kSiMask;
+                    ps[si] = ps[si] * beta + rj[j];
+                }
             }
             // ---- A1 (second half): advance the halo copy of p
 #pragma unroll
@@ -296,6 +347,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_onchip_kernel(CgArgs a, Onchip
             lap(0);
             // ---- A3: q = A p (csr_matvec order), partial p.q
             acc = 0.0;
+            if (PATCH) {
+                if (nval > 0) {
+                    // rolling window over the owned rows: up = row jy-1, cur = row jy, nxt = row jy+1, all NT levels
+                    constexpr int NTP = PATCH ? NT : 1;
+                    double up[NTP], cur[NTP], nxt[NTP];
+                    const double *pb = ps + fresh(sb);
+#pragma unroll
+                    for (int t = 0; t < NTP; t++) { up[t] = pb[t * plane - PX]; cur[t] = pb[t * plane]; }
+#pragma unroll
+                    for (int jy = 0; jy < (PATCH ? YPT : 0); jy++) {
+                        if (jy < nval) {
+#pragma unroll
+                            for (int t = 0; t < NTP; t++) nxt[t] = pb[t * plane + (jy + 1) * PX];
+                            const int ym = (jy == jTop) + (jy == jBot);
+#pragma unroll
+                            for (int t = 0; t < NTP; t++) {
+                                const double *px = pb + t * plane + jy * PX;
+                                const bool tb = t == 0 || t == NTP - 1;
+                                double dg = tb ? dg_tb : dg_ti;
+                                if (ym) dg = dtab[(tb ? 5 : 6) - xmiss - ym - 3];
+                                const double c = cur[t];
+                                double s = 0.0;
+                                if (UNIT) {
+                                    if (t > 0) s -= cur[t - 1];
+                                    s -= up[t]; s -= px[-1];
+                                    s += dg * c;
+                                    s -= px[1]; s -= nxt[t];
+                                    if (t < NTP - 1) s -= cur[t + 1];
+                                } else {
+                                    if (t > 0) s += off * cur[t - 1]; else s += off * 0.0;
+                                    s += off * up[t]; s += off * px[-1];
+                                    s += dg * c;
+                                    s += off * px[1]; s += off * nxt[t];
+                                    if (t < NTP - 1) s += off * cur[t + 1]; else s += off * 0.0;
+                                }
+                                qj[t * YPT + jy] = s;
+                                acc = fma(c, s, acc);
+                            }
+#pragma unroll
+                            for (int t = 0; t < NTP; t++) { up[t] = cur[t]; cur[t] = nxt[t]; }
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
                 const int inf = fresh(info[j]);
@@ -318,6 +413,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_onchip_kernel(CgArgs a, Onchip
                 qj[j] = s;
                 acc = fma(c, s, acc);
             }
+            }
             lap(1);
             const double pq = grid_sum(acc, false, nothing);     // nothing published since the last barrier
             lap(2);
@@ -325,6 +421,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_onchip_kernel(CgArgs a, Onchip
             const double alpha = rr / pq;
             // ---- B: r -= alpha q, export tile edges, partial r.r
             acc = 0.0;
+            if (PATCH) {
+#pragma unroll
+                for (int jy = 0; jy < (PATCH ? YPT : 0); jy++) {
+                    if (jy < nval) {
+#pragma unroll
+                        for (int t = 0; t < NT; t++) {
+                            const int j = t * YPT + jy;
+                            const double v = rj[j] - alpha * qj[j];
+                            rj[j] = v;
+                            acc = fma(v, v, acc);
+                            if (expW) __stcg(qW + t * ty + jy, v);
+                            if (expE) __stcg(qE + t * ty + jy, v);
+                            if (jy == 0 && expN) __stcg(pN + t * tx, v);
+                            if (jy == jS) __stcg(pS + t * tx, v);
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
                 const double v = rj[j] - alpha * qj[j];
@@ -341,13 +455,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_onchip_kernel(CgArgs a, Onchip
                     }
                 }
             }
+            }
             lap(3);
             // split-phase barrier: publish r.r, update x while the other CTAs arrive
             const double rr_new = grid_sum(acc, true, [&] {
+                if (PATCH) {
 #pragma unroll
-                for (int j = 0; j < CPT; j++) {
-                    const int xi = j * NTHREADS + tid;
-                    xs[xi] = xs[xi] + alpha * ps[fresh(info[j]) & kSiMask];
+                    for (int jy = 0; jy < (PATCH ? YPT : 0); jy++) {
+                        if (jy < nval) {
+#pragma unroll
+                            for (int t = 0; t < NT; t++) {
+                                const int xi = (t * YPT + jy) * NTHREADS + tid;
+                                xs[xi] = xs[xi] + alpha * ps[fresh(sb) + t * plane + jy * PX];
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CPT; j++) {
+                        const int xi = j * NTHREADS + tid;
+                        xs[xi] = xs[xi] + alpha * ps[fresh(info[j]) & kSiMask];
+                    }
                 }
                 lap(4);
             });
@@ -358,12 +486,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_onchip_kernel(CgArgs a, Onchip
     }
     if (abort) { if (tid == 0) *a.sync.error = 1; return; }
     // ---- write phi
+    if (PATCH) {
 #pragma unroll
-    for (int j = 0; j < CPT; j++) {
-        if (info[j] & kValid) {
-            const int row = j * RPP + r0;
-            const int t = row / ty, ly = row - t * ty;
-            a.x[((size_t)t * Ny + (y0 + ly)) * Nx + (x0 + lx)] = xs[j * NTHREADS + tid];
+        for (int jy = 0; jy < (PATCH ? YPT : 0); jy++) {
+            if (jy < nval) {
+#pragma unroll
+                for (int t = 0; t < NT; t++)
+                    a.x[((size_t)t * Ny + (y0 + ly0 + jy)) * Nx + (x0 + lx)] = xs[(t * YPT + jy) * NTHREADS + tid];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < CPT; j++) {
+            if (info[j] & kValid) {
+                const int row = j * RPP + r0;
+                const int t = row / ty, ly = row - t * ty;
+                a.x[((size_t)t * Ny + (y0 + ly)) * Nx + (x0 + lx)] = xs[j * NTHREADS + tid];
+            }
         }
     }
     if (cta == 0 && tid == 0) { a.out[0] = it; a.out[1] = status; }
@@ -377,15 +516,17 @@ __global__ void k_fill_u64(unsigned long long *p, int n, unsigned long long v)
 }
 
 // ---- configurations: threads per CTA x cell slots per thread (same per-SM capacity) ----------
-struct Config { int threads, cpt; const void *unit, *general; };
+struct Config { int threads, cpt; const void *unit, *general; int nt, ypt; };   // nt > 0: patch ownership, needs Nt == nt
 const Config kConfigs[] = {
+    // patch ownership for the CLI default Nt = 4
+    {512, 16, (const void *)cg_onchip_kernel<512, 16, true, 4, 4>, (const void *)cg_onchip_kernel<512, 16, false, 4, 4>, 4, 4},
     // measured on B200 at 388x584x4: 8.9 / 9.8 / 10.6 us per CG iteration (ties go to the first)
-    {512, 14, (const void *)cg_onchip_kernel<512, 14, true>, (const void *)cg_onchip_kernel<512, 14, false>},
-    {1024, 7, (const void *)cg_onchip_kernel<1024, 7, true>, (const void *)cg_onchip_kernel<1024, 7, false>},
-    {256, 28, (const void *)cg_onchip_kernel<256, 28, true>, (const void *)cg_onchip_kernel<256, 28, false>},
+    {512, 14, (const void *)cg_onchip_kernel<512, 14, true>, (const void *)cg_onchip_kernel<512, 14, false>, 0, 0},
+    {1024, 7, (const void *)cg_onchip_kernel<1024, 7, true>, (const void *)cg_onchip_kernel<1024, 7, false>, 0, 0},
+    {256, 28, (const void *)cg_onchip_kernel<256, 28, true>, (const void *)cg_onchip_kernel<256, 28, false>, 0, 0},
     // larger per-SM capacity (9 216 / 10 240 cells) for grids such as 480x640x4 that the first three cannot hold
-    {512, 18, (const void *)cg_onchip_kernel<512, 18, true>, (const void *)cg_onchip_kernel<512, 18, false>},
-    {256, 40, (const void *)cg_onchip_kernel<256, 40, true>, (const void *)cg_onchip_kernel<256, 40, false>},
+    {512, 18, (const void *)cg_onchip_kernel<512, 18, true>, (const void *)cg_onchip_kernel<512, 18, false>, 0, 0},
+    {256, 40, (const void *)cg_onchip_kernel<256, 40, true>, (const void *)cg_onchip_kernel<256, 40, false>, 0, 0},
 };
 constexpr int kNumConfigs = sizeof(kConfigs) / sizeof(kConfigs[0]);
 
@@ -416,12 +557,16 @@ Plan make_plan(OnchipScratch &d, int device, int Nt, int Ny, int Nx)
     Plan best;
     if (dev_init(d, device) != FOTO_OK || Nt > kTMask) return best;
     long long best_key = -1;
+    int force_gy = 0, force_gx = 0;                      // FOTO_ONCHIP_GRID=gy,gx: pin the tile grid (experiments)
+    if (const char *e = getenv("FOTO_ONCHIP_GRID")) sscanf(e, "%d,%d", &force_gy, &force_gx);
     for (int c = 0; c < kNumConfigs; c++) {
         if (d.forced_cfg >= 0 && c != d.forced_cfg) continue;
         const int T = kConfigs[c].threads, CPT = kConfigs[c].cpt;
+        if (kConfigs[c].nt > 0 && kConfigs[c].nt != Nt) continue;
         for (int gy = 1; gy <= d.num_sms && gy <= Ny; gy++) {
             const int gx_max = d.num_sms / gy;
             for (int gx = 1; gx <= gx_max && gx <= Nx; gx++) {
+                if (force_gy > 0 && (gy != force_gy || gx != force_gx)) continue;
                 const int ty = (Ny + gy - 1) / gy, tx = (Nx + gx - 1) / gx;      // largest tile
                 const int ty_min = Ny / gy, tx_min = Nx / gx;                   // smallest tile
                 if (tx > T || ty_min < 1 || tx_min < 1) continue;
@@ -441,8 +586,16 @@ Plan make_plan(OnchipScratch &d, int device, int Nt, int Ny, int Nx)
                 // work per SM ~ passes * threads (issue slots); then prefer wide tiles: a warp that
                 // spans several tile rows takes the W/E edge-export path in every cell and has
                 // shared-memory bank conflicts at the row breaks; then short halos
-                const long long edge_warps = 32000 / tx + 2000 / ty;      // ~ per-mille of warps on the edge path
-                const long long key = (((long long)passes * T) * 10000 + edge_warps) * 100000 + (long long)(tx + ty);
+                long long edge_warps = 32000 / tx + 2000 / ty;            // ~ per-mille of warps on the edge path
+                long long work = (long long)passes * T;
+                if (kConfigs[c].nt > 0) {
+                    // patch ownership: an active thread always works on all of its cell slots, so every grid that
+                    // fits costs about the same; measured at 388x584x4 (tools/sweep_grid.py): 7.9-8.1 us for tiles
+                    // wider than tall with ty >= 11, 8.3-8.8 us for very flat (ty = 8) or narrow (tx < 40) tiles; idle SMs cost a little
+                    work = 0;
+                    edge_warps = 32000 / tx + 8000 / ty + 3 * (d.num_sms - gy * gx);
+                }
+                const long long key = (work * 10000 + edge_warps) * 100000 + (long long)(tx + ty);
                 if (best_key < 0 || key < best_key) {
                     best_key = key;
                     best.ok = true; best.cfg = c; best.gy = gy; best.gx = gx; best.ncta = gy * gx;
