@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libfoto_b200.so")
+_SO = os.environ.get("FOTO_B200_LIB") or os.path.join(_HERE, "libfoto_b200.so")   # override: A/B experiments only
 _CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 
 POISSON_CG_PARITY, POISSON_CG_TIGHT, POISSON_DCT_EXACT = 0, 1, 2
