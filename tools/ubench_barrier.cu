@@ -68,6 +68,43 @@ __global__ void __launch_bounds__(512) k_allreduce(unsigned long long *slots, in
     if (tid == 0 && cta == 0) { *cycles = clock64() - t0; *out = total; }
 }
 
+
+// one-hop variant: every CTA pushes its partial into a private inbox of every other CTA ([3][ncta][ncta] words) and
+// polls only its own inbox; all CTAs sum the same values in the same order.
+__global__ void __launch_bounds__(512) k_allgather_push(unsigned long long *inbox, int iters, int fence, long long *cycles, double *out)
+{
+    __shared__ double sh[2];
+    const int tid = threadIdx.x, cta = blockIdx.x, ncta = gridDim.x, lane = tid & 31;
+    double val = cta + 1.0, total = 0.0;
+    long long t0 = clock64();
+    for (unsigned int gen = 0; gen < (unsigned int)iters; gen++) {
+        __syncthreads();
+        if (tid < 32) {
+            unsigned long long *nxt = inbox + (size_t)((gen + 1) % 3) * ncta * ncta, *cur = inbox + (size_t)(gen % 3) * ncta * ncta;
+            for (int d = lane; d < ncta; d += 32) str(nxt + (size_t)d * ncta + cta, SENT);
+            if (fence) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(val);
+            for (int d = lane; d < ncta; d += 32) str(cur + (size_t)d * ncta + cta, bits);
+            const unsigned long long *mine = cur + (size_t)cta * ncta;
+            unsigned long long v[8]; bool ready;
+            do {
+                ready = true;
+#pragma unroll
+                for (int k = 0; k < 8; k++) { int b = k * 32 + lane; v[k] = b < ncta ? ldr(mine + b) : 0ull; ready = ready && v[k] != SENT; }
+            } while (!ready);
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) s += __longlong_as_double((long long)v[k]);
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) sh[0] = s;
+        }
+        __syncthreads();
+        total = sh[0];
+        val = total * 1e-3 + cta;
+    }
+    if (tid == 0 && cta == 0) { *cycles = clock64() - t0; *out = total; }
+}
+
 // one-way signal latency: CTA 0 and CTA `peer` ping-pong a word through L2
 __global__ void k_pingpong(unsigned long long *w, int iters, int peer, long long *cycles)
 {
@@ -99,13 +136,25 @@ int main()
             printf("ping-pong CTA 0 <-> CTA %3d: %.0f cycles per round trip (2 one-way signals)\n", peer, (double)h / iters);
         }
     }
-    for (int bs : {512}) for (int RW : {1, 2, 4, 8}) for (int WW : {1, 2, 4}) for (int REP : {1, 4, 16}) {
+    for (int bs : {512}) for (int RW : {1, 4}) for (int WW : {1, 2}) for (int REP : {1, 4}) {
         k_fill<<<32, 256>>>(slots, 8192, SENT);
         void *args[] = {&slots, &iters, &RW, &WW, &REP, &cyc, &res};
         cudaError_t e = cudaLaunchCooperativeKernel((void *)k_allreduce, dim3(sms), dim3(bs), args, 0, 0);
         cudaDeviceSynchronize();
         long long h; double r; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost); cudaMemcpy(&r, res, 8, cudaMemcpyDeviceToHost);
         printf("allreduce root warps %d, waiter warps %d, bcast replicas %2d: %.0f cycles  [%s, total %.3f]\n", RW, WW, REP, (double)h / iters, cudaGetErrorString(e), r);
+    }
+    {
+        unsigned long long *inbox; const int n = 3 * sms * sms;
+        cudaMalloc(&inbox, (size_t)n * 8);
+        for (int fence : {0, 1}) {
+            k_fill<<<(n + 255) / 256, 256>>>(inbox, n, SENT);
+            void *args[] = {&inbox, &iters, &fence, &cyc, &res};
+            cudaError_t e = cudaLaunchCooperativeKernel((void *)k_allgather_push, dim3(sms), dim3(512), args, 0, 0);
+            cudaDeviceSynchronize();
+            long long h; double r; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost); cudaMemcpy(&r, res, 8, cudaMemcpyDeviceToHost);
+            printf("one-hop push all-gather (private inboxes), fence %d: %.0f cycles  [%s, total %.3f]\n", fence, (double)h / iters, cudaGetErrorString(e), r);
+        }
     }
     printf("last error: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
