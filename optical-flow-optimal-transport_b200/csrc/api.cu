@@ -191,7 +191,7 @@ extern "C" int foto_ctx_reset_stats(foto_ctx *c) { if (!c) return FOTO_ERR_ARG; 
 extern "C" int foto_ctx_get_stats(foto_ctx *c, foto_stats *out) { if (!c || !out) return FOTO_ERR_ARG; *out = c->stats; return FOTO_OK; }
 extern "C" int foto_ctx_set_cg_variant(foto_ctx *c, int v)
 {
-    if (!c || v < -1 || v > 1) { set_error("cg variant must be -1, 0 or 1"); return FOTO_ERR_ARG; }
+    if (!c || v < -1 || v > 2) { set_error("cg variant must be -1, 0, 1 or 2"); return FOTO_ERR_ARG; }
     c->cg_variant = v;
     return FOTO_OK;
 }
@@ -311,14 +311,23 @@ static int run_cg(foto_ctx *c, const Dims &d, const double *F, double *phi, doub
     else { set_error("unknown Poisson back-end %d", backend); return FOTO_ERR_ARG; }
     a.sync.counter = c->sync_counter; a.sync.partials = c->sync_partials; a.sync.error = &c->d_res->error;
     a.out = &c->d_res->cg_iters;
+    // kernel choice: 0 streaming, 1 on-chip (textbook recurrences), 2 on-chip single-reduction, -1 auto = the fastest
+    // that fits (the single-reduction form only for the truncated cg_parity solve it was validated on)
     const bool fits = cg_onchip_fits(c->onchip, c->device, d.Nt, d.Ny, d.Nx);
+    const bool fits_fused = cg_fused_fits(c->onchip, c->device, d.Nt, d.Ny, d.Nx);
     if (c->cg_variant == 1 && !fits) { set_error("grid %dx%dx%d does not fit the on-chip CG variant", d.Nt, d.Ny, d.Nx); return FOTO_ERR_ARG; }
-    const bool onchip = fits && c->cg_variant != 0;
+    if (c->cg_variant == 2 && !fits_fused) { set_error("grid %dx%dx%d does not fit the single-reduction on-chip CG variant", d.Nt, d.Ny, d.Nx); return FOTO_ERR_ARG; }
+    int kind = 0;
+    const char *no_fused = getenv("FOTO_NO_FUSED_CG");      // auto without the single-reduction kernel (tests, A/B runs)
+    const bool auto_fused = c->cg_variant == -1 && fits_fused && backend == FOTO_POISSON_CG_PARITY && !(no_fused && no_fused[0] == '1');
+    if (c->cg_variant == 2 || auto_fused) kind = 3;
+    else if (c->cg_variant != 0 && fits) kind = 1;
     prof_begin(c, CAT_CG);
-    if (onchip) FOTO_TRY(launch_cg_onchip(c->stream, a, c->device, c->onchip));
+    if (kind == 3) FOTO_TRY(launch_cg_fused(c->stream, a, c->device, c->onchip));
+    else if (kind == 1) FOTO_TRY(launch_cg_onchip(c->stream, a, c->device, c->onchip));
     else FOTO_TRY(launch_cg_stream(c->stream, a, c->cg_grid, c->cg_block));
     prof_end(c);
-    c->stats.cg_variant = onchip ? 1 : 0;
+    c->stats.cg_variant = kind;
     c->stats.launches++; c->stats.cg_launches++;
     CUDA_TRY(cudaGetLastError());
     return FOTO_OK;
@@ -438,7 +447,7 @@ static int default_variant()
     if (v == -2) {
         const char *e = getenv("FOTO_CG_VARIANT");
         v = e ? atoi(e) : -1;
-        if (v < -1 || v > 1) v = -1;
+        if (v < -1 || v > 2) v = -1;
         g_default_variant.store(v);
     }
     return v;
@@ -446,7 +455,7 @@ static int default_variant()
 
 extern "C" int foto_set_default_cg_variant(int v)
 {
-    if (v < -1 || v > 1) { set_error("cg variant must be -1, 0 or 1"); return FOTO_ERR_ARG; }
+    if (v < -1 || v > 2) { set_error("cg variant must be -1, 0, 1 or 2"); return FOTO_ERR_ARG; }
     g_default_variant.store(v);
     return FOTO_OK;
 }

@@ -68,6 +68,9 @@ struct OnchipScratch {          // owned by the context
     long long *prof = nullptr;  // 8 cycle counters (debugging aid, see foto_debug_onchip_prof)
     bool attr_set = false;
     int forced_cfg = -1;        // FOTO_ONCHIP_CONFIG: pin one (threads, cells/thread) configuration
+    double *fused_edges = nullptr; size_t fused_edges_bytes = 0;   // cg_fused.cu
+    unsigned long long *fused_slots = nullptr;
+    bool fused_attr_set = false;
     double *gn_edges = nullptr; size_t gn_edges_bytes = 0;      // gn_onchip.cu
     unsigned long long *gn_slots = nullptr;
     bool gn_attr_set = false;
@@ -75,6 +78,9 @@ struct OnchipScratch {          // owned by the context
 bool cg_onchip_fits(OnchipScratch &s, int device, int Nt, int Ny, int Nx);
 int launch_cg_onchip(cudaStream_t st, const CgArgs &a, int device, OnchipScratch &s);
 void cg_onchip_release(OnchipScratch &s);
+// on-chip resident, one grid all-reduce per iteration (Chronopoulos-Gear arrangement, Nt = 4); cg_fused.cu
+bool cg_fused_fits(OnchipScratch &s, int device, int Nt, int Ny, int Nx);
+int launch_cg_fused(cudaStream_t st, const CgArgs &a, int device, OnchipScratch &s);
 
 // ---- exact Poisson solve by separable DCT (dct_kernels.cu) -------------------------------
 struct DctTables {              // device pointers, owned by the context, valid for (Nt, Ny, Nx)

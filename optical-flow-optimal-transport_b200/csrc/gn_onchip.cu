@@ -12,18 +12,11 @@
 // System (classical.py:102-110): A = diag(alpha, alpha, lambda) (x) (-Lap_Neumann) + g g^T, g = (fx, fy, -f2).
 // The reference factorises A (SuperLU); any solve converged far below 1e-9 is a valid stand-in.
 #include "foto_kernels.cuh"
+#include "grid_sync.cuh"
 
 namespace foto {
 
 namespace {
-
-constexpr unsigned long long kSentinel = 0x7FF8DEADBEEF0001ull;
-constexpr unsigned long long kAbort = 0x7FF8DEADBEEF0002ull;
-constexpr unsigned long long kPlainNaN = 0x7FF8000000000000ull;
-constexpr int kNV = 2;                                   // values per all-reduce
-constexpr int kBcastOff = 3 * kNV * kMaxBlocks;          // slots: [3 gen][kNV][kMaxBlocks] partials, then [3][16] totals
-constexpr int kSlotWords = kBcastOff + 3 * 16;
-constexpr long long kWatchdogCycles = 8000000000ll;
 
 struct Geom {
     int gy, gx, maxlen;
@@ -31,85 +24,7 @@ struct Geom {
     unsigned long long *slots;
 };
 
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-__device__ __forceinline__ unsigned long long enc(double v)
-{
-    unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    return (b == kSentinel || b == kAbort) ? kPlainNaN : b;
-}
-
-// grid all-reduce of NV (<= kNV) values: arrive (thread 0), root gather (warp 0 of CTA 0), wait (thread 0).
-template <int NV>
-__device__ __forceinline__ void grid_arrive(const Geom &g, unsigned int gen, const double *v, bool publish)
-{
-#pragma unroll
-    for (int i = 0; i < NV; i++) st_relaxed_u64(g.slots + (((gen + 1u) % 3u) * kNV + i) * kMaxBlocks + blockIdx.x, kSentinel);
-    if (publish) fence_acq_rel_gpu();
-#pragma unroll
-    for (int i = 0; i < NV; i++) st_relaxed_u64(g.slots + ((gen % 3u) * kNV + i) * kMaxBlocks + blockIdx.x, enc(v[i]));
-}
-
-template <int NV>
-__device__ __forceinline__ void grid_root(const Geom &g, unsigned int gen, int ncta, int lane)
-{
-    const long long t0 = clock64();
-    bool abort = false;
-    double tot[NV];
-#pragma unroll
-    for (int i = 0; i < NV; i++) tot[i] = 0.0;
-    const unsigned long long *cur = g.slots + (gen % 3u) * kNV * kMaxBlocks;
-    for (int base = 0; base < ncta; base += 256) {
-        unsigned long long v[NV][8];
-        bool ready;
-        do {                                             // all NV x 8 polls of a lane are in flight together
-            ready = true;
-#pragma unroll
-            for (int i = 0; i < NV; i++)
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int b = base + k * 32 + lane;
-                    v[i][k] = b < ncta ? ld_relaxed_u64(cur + i * kMaxBlocks + b) : 0ull;
-                    ready = ready && v[i][k] != kSentinel;
-                }
-            if (!ready && clock64() - t0 > kWatchdogCycles) { abort = true; break; }
-        } while (!ready);
-#pragma unroll
-        for (int i = 0; i < NV; i++)
-#pragma unroll
-            for (int k = 0; k < 8; k++) tot[i] += __longlong_as_double((long long)v[i][k]);
-    }
-#pragma unroll
-    for (int i = 0; i < NV; i++) tot[i] = warp_sum(tot[i]);
-    abort = __any_sync(0xffffffffu, abort);
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NV; i++) st_relaxed_u64(g.slots + kBcastOff + ((gen + 1u) % 3u) * 16 + i, kSentinel);
-#pragma unroll
-        for (int i = 0; i < NV; i++) st_relaxed_u64(g.slots + kBcastOff + (gen % 3u) * 16 + i, abort ? kAbort : enc(tot[i]));
-    }
-}
-
-// one polling lane per value; returns the bits of value i (kAbort on a watchdog / root abort)
-__device__ __forceinline__ unsigned long long grid_wait(const Geom &g, unsigned int gen, int i)
-{
-    const long long t0 = clock64();
-    const unsigned long long *p = g.slots + kBcastOff + (gen % 3u) * 16 + i;
-    unsigned long long bits;
-    while ((bits = ld_relaxed_u64(p)) == kSentinel) {
-        if (clock64() - t0 > 2 * kWatchdogCycles) { bits = kAbort; break; }
-    }
-    return bits;
-}
+using namespace gsync;
 
 // pixel descriptor: bits 0-15 index of the pixel in one plane of ps, 16-18 neighbour count, 19-22 export N/S/W/E, 23 valid
 constexpr int kSiMask = 0xFFFF, kCntShift = 16;
@@ -212,12 +127,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gn_onchip_kernel(GnArgs a, Geom g
     // run between them; results in every thread
     auto sum_begin = [&](double *v, bool publish) {
         block_sum<2>(reinterpret_cast<double(&)[2]>(*v), red);
-        if (tid == 0) grid_arrive<2>(g, gen, v, publish);
+        if (tid == 0) grid_arrive<2>(g.slots, gen, v, publish);
     };
     auto sum_end = [&](double *v) {
-        if (cta == 0 && tid < 32) grid_root<2>(g, gen, ncta, tid);
+        if (cta == 0 && tid < 32) grid_root<2>(g.slots, gen, ncta, tid);
         if (tid < 2) {
-            const unsigned long long bits = grid_wait(g, gen, tid);
+            const unsigned long long bits = grid_wait(g.slots, gen, tid);
             red[64 + tid] = __longlong_as_double((long long)bits);
             if (bits == kAbort) red[66] = 1.0;
         }

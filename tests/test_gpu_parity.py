@@ -20,12 +20,19 @@ DEGENERATE = {"foto_31x29_nt2", "foto_squares32"}     # see tests/test_oracle_go
 DEGENERATE_TOL = 5e-8
 
 
-@pytest.fixture(params=["onchip_or_auto", "streaming"], autouse=True)
+@pytest.fixture(params=["onchip_or_auto", "onchip_textbook", "streaming"], autouse=True)
 def cg_variant(request):
-    """Every test runs twice: with the on-chip resident CG (auto: used whenever the grid fits one
-    tile per SM) and with the streaming CG forced."""
-    foto_b200.set_default_cg_variant(0 if request.param == "streaming" else -1)
+    """Every test runs three times: auto (single-reduction on-chip CG when Nt = 4 and the grid fits one tile per
+    SM, else the textbook on-chip kernel, else streaming), the textbook on-chip CG forced where it fits, and the
+    streaming CG forced."""
+    if request.param == "onchip_textbook":
+        foto_b200.set_default_cg_variant(-1)
+        os.environ["FOTO_NO_FUSED_CG"] = "1"
+    else:
+        os.environ.pop("FOTO_NO_FUSED_CG", None)
+        foto_b200.set_default_cg_variant(0 if request.param == "streaming" else -1)
     yield request.param
+    os.environ.pop("FOTO_NO_FUSED_CG", None)
     foto_b200.set_default_cg_variant(-1)
 
 
@@ -600,4 +607,29 @@ def test_gn_onchip_matches_streaming_many_shapes():
         assert abs(res[0][0] - res[-1][0]) <= 1, (h, w, res[0][0], res[-1][0])
         scale = np.abs(res[0][1]).max() + 1e-300
         assert np.abs(res[0][1] - res[-1][1]).max() <= 1e-11 * scale, (h, w)
+    ctx.close()
+
+
+def test_cg_kernel_selection(cg_variant):
+    """Which Poisson kernel ran (stats.cg_variant): auto takes the single-reduction on-chip kernel for the
+    truncated cg_parity solve at Nt = 4 when the grid fits, the textbook on-chip kernel for other Nt and for
+    cg_tight, the streaming kernel when nothing fits; forcing a kernel that does not fit fails loudly."""
+    import torch
+    ctx = foto_b200.Context(0)
+    expect = {"onchip_or_auto": (3, 1, 1), "onchip_textbook": (1, 1, 1), "streaming": (0, 0, 0)}[cg_variant]
+    ctx.set_cg_variant(0 if cg_variant == "streaming" else -1)
+    def run(h, w, Nt, backend=foto_b200.POISSON_CG_PARITY):
+        f0, f1 = synth.make_pair(h, w, seed=2)
+        d0 = torch.from_numpy(f0).cuda(); d1 = torch.from_numpy(f1).cuda()
+        o = [torch.empty(h * w, dtype=torch.float64, device="cuda") for _ in range(3)]
+        ctx.solve_dev(d0.data_ptr(), d1.data_ptr(), Nt, w, h, *[t.data_ptr() for t in o], max_it=1, backend=backend)
+        return ctx.stats()["cg_variant"]
+    assert run(97, 146, 4) == expect[0]
+    assert run(97, 146, 5) == expect[1]
+    assert run(97, 146, 4, foto_b200.POISSON_CG_TIGHT) == expect[2]
+    assert run(540, 960, 4) == 0                                   # 2 M cells: nothing on-chip fits
+    ctx.set_cg_variant(2)
+    with pytest.raises(ValueError, match="does not fit"):
+        run(97, 146, 5)
+    assert run(97, 146, 4) == 3
     ctx.close()

@@ -18,7 +18,7 @@ d0 = torch.from_numpy(f0).cuda(); d1 = torch.from_numpy(f1).cuda()
 du, dv, dm = (torch.empty(P, dtype=torch.float64, device="cuda") for _ in range(3))
 kw = dict(r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=100)
 res = {}
-for variant, cfg in ((0, None), (1, 0), (1, 1), (1, 2)):
+for variant, cfg in ((0, None), (2, None), (1, 0), (1, 1)):
     if cfg is not None:
         os.environ["FOTO_ONCHIP_CONFIG"] = str(cfg)
     ctx = foto_b200.Context(0)
@@ -27,18 +27,22 @@ for variant, cfg in ((0, None), (1, 0), (1, 1), (1, 2)):
     ctx.set_profiling(True); ctx.reset_stats()
     info = ctx.solve_dev(d0.data_ptr(), d1.data_ptr(), Nt, w, h, du.data_ptr(), dv.data_ptr(), dm.data_ptr(), **kw)
     st = ctx.stats()
-    if variant == 1:          # second run with the in-kernel phase counters on (slightly intrusive)
+    if variant >= 1:          # second run with the in-kernel phase counters on (slightly intrusive)
         ctx.onchip_prof(True)
         ctx.solve_dev(d0.data_ptr(), d1.data_ptr(), Nt, w, h, du.data_ptr(), dv.data_ptr(), dm.data_ptr(), **kw)
     res[variant] = du.cpu().numpy().copy()
     print(f"variant {variant} config {cfg}: outer {info['n_outer']} cg {info['cg_iters'].tolist()} "
           f"cg_ms {st['cg_ms']:.3f} us/iter {1e3 * st['cg_ms'] / st['cg_iterations']:.3f}")
-    if variant == 1:
+    if variant >= 1:
         c = ctx.onchip_prof(False)
         c = c[c[:, 6] > 0].astype(float)
         it = c[:, 6:7]
         names = ["halo+p update", "stencil", "barrier1", "r update+edges", "x update(+gather)", "barrier2 wait"]
+        if variant == 2:
+            names = ["halo import (spin)", "stencil", "all-reduce (+x/2)", "p,s,r update+export", "x/2 (hop)", "-"]
         per = c[:, :6] / it
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        np.savetxt(os.path.join(ROOT, "gpurun_out", f"phase_cycles_variant{variant}_cfg{cfg}.csv"), per, fmt="%.0f", delimiter=",")
         print(f"   {len(c)} CTAs, cycles/iteration      CTA0      min   median      max   argmax")
         for k, n in enumerate(names):
             col = per[:, k]
@@ -47,6 +51,6 @@ for variant, cfg in ((0, None), (1, 0), (1, 1), (1, 2)):
         print(f"   {'total':20s} {tot[0]:9.0f} {tot.min():8.0f} {np.median(tot):8.0f} {tot.max():8.0f}")
         comp = per[:, [0, 1, 3]].sum(axis=1)
         print(f"   compute (no barriers, no x): min {comp.min():.0f} median {np.median(comp):.0f} max {comp.max():.0f} at CTA {int(comp.argmax())}")
-    if variant == 1:
-        print("   max |u_onchip - u_stream| / max|u| =", float(np.max(np.abs(res[0] - res[1])) / np.max(np.abs(res[0]))))
+    if variant >= 1:
+        print("   max |u_onchip - u_stream| / max|u| =", float(np.max(np.abs(res[0] - res[variant])) / np.max(np.abs(res[0]))))
     ctx.close()

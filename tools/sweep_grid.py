@@ -12,7 +12,7 @@ o = [torch.empty(h * w, dtype=torch.float64, device="cuda") for _ in range(3)]
 kw = dict(r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=100)
 for cfg in os.environ.get("SWEEP_CONFIGS", "0").split(","):
     os.environ["FOTO_ONCHIP_CONFIG"] = cfg
-    ctx = foto_b200.Context(0); ctx.set_cg_variant(1)
+    ctx = foto_b200.Context(0); ctx.set_cg_variant(int(os.environ.get("SWEEP_VARIANT", "1")))
     for g in grids:
         os.environ["FOTO_ONCHIP_GRID"] = g
         try:
