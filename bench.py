@@ -39,6 +39,7 @@ H, W, NT = 388, 584, 4
 PARAMS = dict(r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=100)
 P = H * W
 N = NT * P
+CG_KERNEL_NAMES = {0: "cg_stream_kernel", 1: "cg_onchip_kernel", 3: "cg_fused_kernel"}   # foto_stats.cg_variant
 CG_BYTES_PER_CELL_ITER = 88      # 11 fp64 words per cell per CG iteration
 RHS_BYTES_PER_CELL = 56
 PROX_BYTES_PER_CELL = 80
@@ -294,7 +295,7 @@ def run_b200(args):
         traffic, traffic_src = None, None            # DRAM bytes per launch from the committed ncu --set full capture
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            t = json.load(open(tpath)).get("cg_onchip_kernel" if stats["cg_variant"] == 1 else "cg_stream_kernel")
+            t = json.load(open(tpath)).get(CG_KERNEL_NAMES.get(stats["cg_variant"], "cg_stream_kernel"))
             if t:
                 traffic, traffic_src = t["dram_bytes_per_launch"], t["source"]
         per_launch_iters = stats["cg_iterations"] / max(stats["cg_launches"], 1)
@@ -305,7 +306,8 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "foto_388x584_nt4_cli_defaults", "pairs_per_gpu_per_step": B,
                        "params": PARAMS, "poisson_backend": "cg_parity",
-                       "cg_variant": "on-chip" if stats["cg_variant"] == 1 else "streaming",
+                       "cg_variant": {0: "streaming", 1: "on-chip (textbook recurrences, 2 all-reduces/iteration)",
+                                      3: "on-chip single-reduction (Chronopoulos-Gear arrangement)"}.get(stats["cg_variant"], "?"),
                        "l2": "512 MB device memset between steps (working set 87 MB/pair < 126 MB L2)",
                        "outer_iterations_per_pair": statistics.mean(outer_counts) if outer_counts else None},
             "outer_iters_per_s": world * stats["cg_launches"] / (dev_ms / 1e3),
@@ -315,7 +317,7 @@ def run_b200(args):
                     "timing": "wall clock around foto_solve_host calls, pinned host buffers"},
             "gpu_launches": int(stats["launches"]),
             "clocks": clocks,
-            "roofline": {"kernel": "cg_onchip_kernel" if stats["cg_variant"] == 1 else "cg_stream_kernel",
+            "roofline": {"kernel": CG_KERNEL_NAMES.get(stats["cg_variant"], "cg_stream_kernel"),
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": CG_BYTES_PER_CELL_ITER * N * per_launch_iters,

@@ -258,7 +258,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
         lap(1);
         // ---- the one all-reduce; the x update of the previous iteration runs in its shadow
         block_sum<2>(acc, red);
+#ifdef FOTO_PARANOID_FENCES
+        if (tid == 0) grid_arrive<2>(g.slots, gen, acc, true);      // orders this CTA's halo reads before the neighbours' next export
+#else
         if (tid == 0) grid_arrive<2>(g.slots, gen, acc, false);
+#endif
         if (cta == 0 && tid < 32) grid_root<2>(g.slots, gen, ncta, tid);
         if (pend) {                                      // second half of x += alpha_prev p (first half: after the export)
 #pragma unroll
@@ -343,8 +347,10 @@ constexpr int kThreads = 512, kNT = 4, kYPT = 4;
 struct Plan { bool ok = false; int gy = 0, gx = 0, maxlen = 0, ncta = 0; size_t smem = 0; };
 
 // Tile grid: gy*gx <= #SMs, every tile fits the 4 x 4 patches of 512 threads, the halo tables and shared memory.
-// Every grid that fits costs about the same (an active thread always works on its 16 cell slots); prefer tiles that
-// are wider than tall but not flat, and few idle SMs (tools/sweep_grid.py).
+// Every grid that fits costs an active thread the same 16 cell slots; what differs is measured (tools/sweep_grid.py,
+// 388x584x4, SWEEP_VARIANT=2: 5.87 us per iteration for 12x12, 5.96 for 8x18, 6.2-6.6 for the rest): tiles whose
+// width is a multiple of 16 (+1) keep a half-warp inside one row group, i.e. free of shared-memory bank conflicts;
+// then short halos and few idle SMs; then wide rows.
 Plan make_plan(OnchipScratch &d, int device, int Nt, int Ny, int Nx)
 {
     Plan best;
@@ -369,7 +375,8 @@ Plan make_plan(OnchipScratch &d, int device, int Nt, int Ny, int Nx)
             const size_t smem = ((((size_t)kNT * (ty + 2) * (tx + 2) + 1) & ~size_t(1)) + (size_t)2 * kNT * kYPT * kThreads + 80 + 4) * 8
                               + (size_t)8 * kNT * (tx + ty) * sizeof(int);
             if (smem > d.smem_optin) continue;
-            const long long key = (32000 / tx + 8000 / ty + 3 * (d.num_sms - gy * gx)) * 100000LL + (tx + ty);
+            const int straddle = (tx % 16) > 1 ? 1 : 0;
+            const long long key = ((straddle * 100000LL + 2LL * kNT * (tx + ty) + 8LL * (d.num_sms - gy * gx)) * 1000) + (999 - tx);
             if (best_key < 0 || key < best_key) {
                 best_key = key; best.ok = true; best.gy = gy; best.gx = gx; best.ncta = gy * gx;
                 best.maxlen = tx > ty ? tx : ty; best.smem = smem;

@@ -8,6 +8,7 @@
 // arrive: thread 0 of every CTA (after a __syncthreads that follows the CTA's global writes when `publish`);
 // root:   warp 0 of CTA 0 sums the partials in a fixed order and writes the totals;
 // wait:   lane i of warp 0 polls total i.   Every CTA gets bit-identical totals.
+// Readers rely on a control-dependent poll followed by __syncthreads; -DFOTO_PARANOID_FENCES adds the acquire fences.
 #pragma once
 #include "common.cuh"
 
@@ -80,6 +81,9 @@ __device__ __forceinline__ void grid_root(unsigned long long *slots, unsigned in
 #pragma unroll
             for (int k = 0; k < 8; k++) tot[i] += __longlong_as_double((long long)v[i][k]);
     }
+#ifdef FOTO_PARANOID_FENCES
+    fence_acq_rel_gpu();                                 // acquire the partials, release the totals
+#endif
 #pragma unroll
     for (int i = 0; i < NV; i++) tot[i] = warp_sum(tot[i]);
     abort = __any_sync(0xffffffffu, abort);
@@ -100,6 +104,9 @@ __device__ __forceinline__ unsigned long long grid_wait(unsigned long long *slot
     while ((bits = ld_relaxed_u64(p)) == kSentinel) {
         if (clock64() - t0 > 2 * kWatchdogCycles) { bits = kAbort; break; }
     }
+#ifdef FOTO_PARANOID_FENCES
+    fence_acq_rel_gpu();
+#endif
     return bits;
 }
 
