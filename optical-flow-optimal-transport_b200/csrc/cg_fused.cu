@@ -342,9 +342,15 @@ __global__ void k_fill2_u64(unsigned long long *p, int n, unsigned long long v, 
     if (i < m) q[i] = w;
 }
 
-constexpr int kThreads = 512, kNT = 4, kYPT = 4;
+constexpr int kThreads = 512;
+// patch shapes: NT time levels x YPT rows per thread (<= 16 cell slots: p and s take 4 registers per slot, the
+// stencil window 6 NT); Nt = 4 is the CLI default and the benchmark configuration
+struct Shape { int nt, ypt; const void *unit, *general; };
+#define FOTO_FUSED_SHAPE(NT, YPT) {NT, YPT, (const void *)cg_fused_kernel<kThreads, NT, YPT, true>, (const void *)cg_fused_kernel<kThreads, NT, YPT, false>}
+const Shape kShapes[] = {FOTO_FUSED_SHAPE(2, 8), FOTO_FUSED_SHAPE(3, 5), FOTO_FUSED_SHAPE(4, 4), FOTO_FUSED_SHAPE(5, 3)};
+constexpr int kNumShapes = sizeof(kShapes) / sizeof(kShapes[0]);
 
-struct Plan { bool ok = false; int gy = 0, gx = 0, maxlen = 0, ncta = 0; size_t smem = 0; };
+struct Plan { bool ok = false; int shape = 0, gy = 0, gx = 0, maxlen = 0, ncta = 0; size_t smem = 0; };
 
 // Tile grid: gy*gx <= #SMs, every tile fits the 4 x 4 patches of 512 threads, the halo tables and shared memory.
 // Every grid that fits costs an active thread the same 16 cell slots; what differs is measured (tools/sweep_grid.py,
@@ -354,7 +360,11 @@ struct Plan { bool ok = false; int gy = 0, gx = 0, maxlen = 0, ncta = 0; size_t 
 Plan make_plan(OnchipScratch &d, int device, int Nt, int Ny, int Nx)
 {
     Plan best;
-    if (Nt != kNT) return best;
+    int shape = -1;
+    for (int i = 0; i < kNumShapes; i++) if (kShapes[i].nt == Nt) shape = i;
+    if (shape < 0) return best;
+    const int kNT = Nt, kYPT = kShapes[shape].ypt;
+    best.shape = shape;
     if (!d.num_sms) {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return best;
@@ -393,17 +403,19 @@ int launch_cg_fused(cudaStream_t st, const CgArgs &a, int device, OnchipScratch 
 {
     Plan p = make_plan(d, device, a.Nt, a.Ny, a.Nx);
     if (!p.ok) { set_error("grid %dx%dx%d does not fit the single-reduction on-chip CG variant", a.Nt, a.Ny, a.Nx); return FOTO_ERR_ARG; }
-    const size_t need = (size_t)p.ncta * 4 * kNT * p.maxlen * sizeof(double);
+    const size_t need = (size_t)p.ncta * 4 * a.Nt * p.maxlen * sizeof(double);
     if (d.fused_edges_bytes < need) {
         if (d.fused_edges) CUDA_TRY(cudaFree(d.fused_edges));
         CUDA_TRY(cudaMalloc((void **)&d.fused_edges, need));
         d.fused_edges_bytes = need;
     }
     if (!d.fused_slots) CUDA_TRY(cudaMalloc((void **)&d.fused_slots, kSlotWords * sizeof(unsigned long long)));
-    const void *fn = a.rcoef == 1.0 ? (const void *)cg_fused_kernel<kThreads, kNT, kYPT, true> : (const void *)cg_fused_kernel<kThreads, kNT, kYPT, false>;
+    const void *fn = a.rcoef == 1.0 ? kShapes[p.shape].unit : kShapes[p.shape].general;
     if (!d.fused_attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute((const void *)cg_fused_kernel<kThreads, kNT, kYPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_optin));
-        CUDA_TRY(cudaFuncSetAttribute((const void *)cg_fused_kernel<kThreads, kNT, kYPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_optin));
+        for (int i = 0; i < kNumShapes; i++) {
+            CUDA_TRY(cudaFuncSetAttribute(kShapes[i].unit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_optin));
+            CUDA_TRY(cudaFuncSetAttribute(kShapes[i].general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_optin));
+        }
         d.fused_attr_set = true;
     }
     const int nedge = (int)(need / sizeof(double));
