@@ -171,7 +171,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------ CUDA arm
@@ -340,7 +340,7 @@ def run_b200(args):
             line["roofline_streaming_hd"] = hd_roofline(ctx, torch, dev, peak)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single()
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -371,6 +371,9 @@ def hd_roofline(ctx, torch, dev, peak):
             "K3_prox_dual": {"achieved": k3, "frac": k3 / peak, "ms": st["prox_ms"]}}
 
 
+_OUT = sys.stdout
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -378,10 +381,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=4)
-    ap.add_argument("--cg-variant", type=int, default=None, help="-1 auto, 0 streaming, 1 on-chip")
+    ap.add_argument("--cg-variant", type=int, default=None, help="-1 auto, 0 streaming, 1 on-chip textbook, 2 on-chip single-reduction")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hd", action="store_true", help="skip the 1080x1920x16 streaming-roofline measurement")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner under NCCL_DEBUG=VERSION)
+    # are sent to stderr at the file-descriptor level, the JSON goes to the saved descriptor
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
