@@ -392,27 +392,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_onchip_kernel(CgArgs a, Onchip
                 }
             } else {
 #pragma unroll
-            for (int j = 0; j < CPT; j++) {
-                const int inf = fresh(info[j]);
-                const double *pc = ps + (inf & kSiMask);
-                const int code = (inf >> kCntShift) & 3;
-                double dg = dg_interior;                 // 6 neighbours: no shared-memory lookup
-                if (code != 3) dg = dtab[code];
-                const double c = pc[0];
-                double s = 0.0;
-                if (UNIT) {                           // r == 1: products with -1.0 are exact negations
-                    s -= pc[-plane]; s -= pc[-PX]; s -= pc[-1];
-                    s += dg * c;
-                    s -= pc[1]; s -= pc[PX]; s -= pc[plane];
-                } else {
-                    s += off * pc[-plane]; s += off * pc[-PX]; s += off * pc[-1];
-                    s += dg * c;
-                    s += off * pc[1]; s += off * pc[PX]; s += off * pc[plane];
+                for (int j = 0; j < CPT; j++) {
+                    const int inf = fresh(info[j]);
+                    const double *pc = ps + (inf & kSiMask);
+                    const int code = (inf >> kCntShift) & 3;
+                    double dg = dg_interior;                 // 6 neighbours: no shared-memory lookup
+                    if (code != 3) dg = dtab[code];
+                    const double c = pc[0];
+                    double s = 0.0;
+                    if (UNIT) {                           // r == 1: products with -1.0 are exact negations
+                        s -= pc[-plane]; s -= pc[-PX]; s -= pc[-1];
+                        s += dg * c;
+                        s -= pc[1]; s -= pc[PX]; s -= pc[plane];
+                    } else {
+                        s += off * pc[-plane]; s += off * pc[-PX]; s += off * pc[-1];
+                        s += dg * c;
+                        s += off * pc[1]; s += off * pc[PX]; s += off * pc[plane];
+                    }
+                    s = (inf & kValid) ? s : 0.0;
+                    qj[j] = s;
+                    acc = fma(c, s, acc);
                 }
-                s = (inf & kValid) ? s : 0.0;
-                qj[j] = s;
-                acc = fma(c, s, acc);
-            }
             }
             lap(1);
             const double pq = grid_sum(acc, false, nothing);     // nothing published since the last barrier
@@ -440,21 +440,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_onchip_kernel(CgArgs a, Onchip
                 }
             } else {
 #pragma unroll
-            for (int j = 0; j < CPT; j++) {
-                const double v = rj[j] - alpha * qj[j];
-                rj[j] = v;
-                acc = fma(v, v, acc);
-                const int inf = info[j];
-                if (inf & kEdgeAny) {                    // rare path; precomputed pointers keep it short
-                    if (inf & kEdgeW) __stcg(pW + j * RPP, v);
-                    if (inf & kEdgeE) __stcg(pE + j * RPP, v);
-                    if (inf & (kEdgeN | kEdgeS)) {
-                        const int o = ((inf >> kTShift) & kTMask) * tx;
-                        if (inf & kEdgeN) __stcg(pN + o, v);
-                        if (inf & kEdgeS) __stcg(pS + o, v);
+                for (int j = 0; j < CPT; j++) {
+                    const double v = rj[j] - alpha * qj[j];
+                    rj[j] = v;
+                    acc = fma(v, v, acc);
+                    const int inf = info[j];
+                    if (inf & kEdgeAny) {                    // rare path; precomputed pointers keep it short
+                        if (inf & kEdgeW) __stcg(pW + j * RPP, v);
+                        if (inf & kEdgeE) __stcg(pE + j * RPP, v);
+                        if (inf & (kEdgeN | kEdgeS)) {
+                            const int o = ((inf >> kTShift) & kTMask) * tx;
+                            if (inf & kEdgeN) __stcg(pN + o, v);
+                            if (inf & kEdgeS) __stcg(pS + o, v);
+                        }
                     }
                 }
-            }
             }
             lap(3);
             // split-phase barrier: publish r.r, update x while the other CTAs arrive
