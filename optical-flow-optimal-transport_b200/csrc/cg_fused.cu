@@ -7,7 +7,7 @@
 //
 //     w = A r,  gamma = r.r,  delta = r.w                      <- one all-reduce of (gamma, delta)
 //     stop if sqrt(gamma) < atol                                  (scipy's test, same place in the sequence)
-//     beta = gamma / gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old)
+//     beta = gamma / gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old)   [= gamma / (delta - beta^2 d_old)]
 //     p = r + beta p,  s = w + beta s  (= A p),  x += alpha p,  r -= alpha s
 //
 // In exact arithmetic x_k, r_k, alpha_k, beta_k are those of the textbook form; in floating point A p is carried by
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
     auto lap = [&](int k) { if (prof) { long long now = clock64(); sprof[k] += now - tmark; tmark = now; } };
 
     int it = 0, status = a.maxiter;
-    double atol = 0.0, gam_prev = 0.0, alpha_prev = 0.0;
+    double gam_stop = 0.0, rgam_prev = 0.0, d_prev = 0.0, alpha_prev = 0.0;
     bool pend = false;                                   // x += alpha_prev p not yet applied
     if (prof) tmark = clock64();
     for (; it < a.maxiter; it++) {
@@ -285,11 +285,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
         if (abort) break;
         if (it == 0) {
             if (gam == 0.0) { status = 0; break; }       // scipy: "if bnrm2 == 0: return b, 0"
-            atol = a.rtol * sqrt(gam);
+            // scipy stops when sqrt(gamma) < atol, atol = rtol sqrt(gamma_0).  sqrt is monotone and correctly rounded,
+            // so that is gamma < gam_stop with gam_stop the smallest double whose square root reaches atol: found once,
+            // the per-iteration test is then a comparison (no sqrt on the critical path)
+            const double atol = a.rtol * sqrt(gam);
+            double t = atol * atol;
+            for (int k = 0; k < 8 && sqrt(t) < atol; k++) t = __longlong_as_double(__double_as_longlong(t) + 1);
+            for (int k = 0; k < 8 && t > 0.0 && sqrt(__longlong_as_double(__double_as_longlong(t) - 1)) >= atol; k++)
+                t = __longlong_as_double(__double_as_longlong(t) - 1);
+            gam_stop = t;
         }
-        if (sqrt(gam) < atol) { status = 0; break; }     // scipy's "||r|| < atol" at the top of the iteration
-        double beta = 0.0, alpha = gam / del;
-        if (it > 0) { beta = gam / gam_prev; alpha = gam / (del - (beta * gam) / alpha_prev); }
+        if (gam < gam_stop) { status = 0; break; }       // scipy's "||r|| < atol" at the top of the iteration
+        // beta = gamma / gamma_old with the reciprocal taken in the shadow of the all-reduce; with d = gamma / alpha:
+        // d = delta - beta^2 d_old (= delta - beta gamma / alpha_old), alpha = gamma / d: one division after the barrier
+        const double beta = gam * rgam_prev;
+        const double dk = del - (beta * beta) * d_prev;
+        const double alpha = gam / dk;
         // ---- p = r + beta p, s = w + beta s, r -= alpha s; tile-edge values exported as generation it+1
 #pragma unroll
         for (int jy = 0; jy < YPT; jy++) {
@@ -315,7 +326,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
             xs[xi] = xs[xi] + alpha * pj[j];
         }
         lap(4);
-        pend = true; alpha_prev = alpha; gam_prev = gam;
+        pend = true; alpha_prev = alpha; d_prev = dk;
+        rgam_prev = 1.0 / gam;                           // not needed before the next all-reduce has completed
     }
     if (abort) { if (tid == 0) *a.sync.error = 1; return; }
     // ---- write phi (apply the update that was still waiting for a barrier shadow: only after maxiter iterations)
