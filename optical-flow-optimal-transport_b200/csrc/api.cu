@@ -416,9 +416,16 @@ extern "C" int foto_gn_solve_dev(foto_ctx *c, const double *d_f1, const double *
     a.out = &c->d_res->cg_iters;
     launch_gn_coeffs(c->stream, w, h, d_f1, d_f2, alpha, lambda, fx, fy, dinv, b);
     prof_begin(c, CAT_GN);
+    // kernel choice as for the Poisson solve: 0 streaming, 1 on-chip (two all-reduces), 2 on-chip single-reduction,
+    // -1 auto = the fastest that fits
     const bool gn_fits = gn_onchip_fits(c->onchip, c->device, h, w);
+    const bool gnf_fits = gn_fused_fits(c->onchip, c->device, h, w);
     if (c->cg_variant == 1 && !gn_fits) { set_error("image %dx%d does not fit the on-chip GN variant", h, w); return FOTO_ERR_ARG; }
-    if (gn_fits && c->cg_variant != 0) { FOTO_TRY(launch_gn_onchip(c->stream, a, c->device, c->onchip)); c->stats.launches++; }
+    if (c->cg_variant == 2 && !gnf_fits) { set_error("image %dx%d does not fit the single-reduction on-chip GN variant", h, w); return FOTO_ERR_ARG; }
+    const char *no_fused = getenv("FOTO_NO_FUSED_CG");
+    const bool auto_fused = c->cg_variant == -1 && gnf_fits && !(no_fused && no_fused[0] == '1');
+    if (c->cg_variant == 2 || auto_fused) { FOTO_TRY(launch_gn_fused(c->stream, a, c->device, c->onchip)); c->stats.launches++; }
+    else if (gn_fits && c->cg_variant != 0) { FOTO_TRY(launch_gn_onchip(c->stream, a, c->device, c->onchip)); c->stats.launches++; }
     else FOTO_TRY(launch_gn_pcg(c->stream, a, c->gn_grid, c->gn_block));
     prof_end(c);
     c->stats.launches += 2; c->stats.gn_launches++;

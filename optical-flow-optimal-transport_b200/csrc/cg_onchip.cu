@@ -617,7 +617,8 @@ bool cg_onchip_fits(OnchipScratch &s, int device, int Nt, int Ny, int Nx)
 
 void cg_onchip_release(OnchipScratch &s)
 {
-    cudaFree(s.edges); cudaFree(s.slots); cudaFree(s.prof); cudaFree(s.gn_edges); cudaFree(s.gn_slots); cudaFree(s.fused_edges); cudaFree(s.fused_slots);
+    cudaFree(s.edges); cudaFree(s.slots); cudaFree(s.prof); cudaFree(s.gn_edges); cudaFree(s.gn_slots); cudaFree(s.fused_edges); cudaFree(s.fused_slots); cudaFree(s.gnf_edges); cudaFree(s.gnf_slots);
+    s.gnf_edges = nullptr; s.gnf_slots = nullptr; s.gnf_edges_bytes = 0;
     s.fused_edges = nullptr; s.fused_slots = nullptr; s.fused_edges_bytes = 0;
     s.gn_edges = nullptr; s.gn_slots = nullptr; s.gn_edges_bytes = 0;
     s.prof = nullptr;

@@ -71,6 +71,9 @@ struct OnchipScratch {          // owned by the context
     double *fused_edges = nullptr; size_t fused_edges_bytes = 0;   // cg_fused.cu
     unsigned long long *fused_slots = nullptr;
     bool fused_attr_set = false;
+    double *gnf_edges = nullptr; size_t gnf_edges_bytes = 0;    // gn_fused.cu
+    unsigned long long *gnf_slots = nullptr;
+    bool gnf_attr_set = false;
     double *gn_edges = nullptr; size_t gn_edges_bytes = 0;      // gn_onchip.cu
     unsigned long long *gn_slots = nullptr;
     bool gn_attr_set = false;
@@ -117,5 +120,8 @@ int launch_gn_pcg(cudaStream_t st, const GnArgs &a, int grid, int block);
 // on-chip resident variant (gn_onchip.cu): uses fx, fy, f2, dinv, b, x, out, sync.error of GnArgs only
 bool gn_onchip_fits(OnchipScratch &s, int device, int h, int w);
 int launch_gn_onchip(cudaStream_t st, const GnArgs &a, int device, OnchipScratch &s);
+// on-chip resident, one grid all-reduce per iteration (gn_fused.cu)
+bool gn_fused_fits(OnchipScratch &s, int device, int h, int w);
+int launch_gn_fused(cudaStream_t st, const GnArgs &a, int device, OnchipScratch &s);
 
 }  // namespace foto

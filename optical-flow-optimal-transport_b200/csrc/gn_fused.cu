@@ -1,0 +1,358 @@
+// gn_fused.cu -- K6, on-chip resident Jacobi-PCG for the Gennert-Negahdaripour system with ONE grid all-reduce per
+// iteration (the arrangement of cg_fused.cu, here with a preconditioner):
+//
+//     u = D^-1 r,  w = A u,  gamma = r.u,  delta = w.u,  rho = r.r     <- one all-reduce of (gamma, delta, rho)
+//     stop if sqrt(rho) <= rtol ||b||
+//     beta = gamma / gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old)
+//     p = u + beta p,  s = w + beta s (= A p),  x += alpha p,  r -= alpha s
+//
+// The reference factorises A (SuperLU, classical.py:126), so the solve is not tied to a particular Krylov sequence:
+// any iteration converged to rtol = 1e-13 is a valid stand-in (tests: 1e-9 against the direct solve).
+// A = diag(alpha, alpha, lambda) (x) (-Lap_Neumann) + g g^T, g = (fx, fy, -f2)   (classical.py:102-110).
+//
+// One CTA per (y, x) tile, a thread owns up to PPT pixels with all three unknowns.  u lives in shared memory with a
+// halo ring (three planes), x, w and g in private shared-memory slots, r, p, s in registers; D^-1 is re-read from
+// global memory (L2 resident, 3 words per pixel and iteration) because shared memory is full.  Tile-edge values of u
+// travel through L2 tagged with the parity of their generation in the mantissa LSB (no barrier, no fence; see
+// cg_fused.cu), export and import are table-driven passes.
+#include "foto_kernels.cuh"
+#include "grid_sync.cuh"
+
+namespace foto {
+
+namespace {
+
+using namespace gsync;
+
+struct Geom {
+    int gy, gx, maxlen;
+    double *edges;                 // [ncta][4 (N,S,W,E)][3 * maxlen] tile-edge values of u, LSB = generation parity
+    unsigned long long *slots;
+};
+
+constexpr int kHaloPerThread = 4;
+
+template <int NTHREADS, int PPT>
+__global__ void __launch_bounds__(NTHREADS, 1) gn_fused_kernel(GnArgs a, Geom g)
+{
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, cta = blockIdx.x, ncta = gridDim.x;
+    const int w = a.w, h = a.h;
+    const int by = cta / g.gx, bx = cta - by * g.gx;
+    const int y0 = (int)((long long)by * h / g.gy), y1 = (int)((long long)(by + 1) * h / g.gy);
+    const int x0 = (int)((long long)bx * w / g.gx), x1 = (int)((long long)(bx + 1) * w / g.gx);
+    const int ty = y1 - y0, tx = x1 - x0, PX = tx + 2, PY = ty + 2, plane = PY * PX;
+    const int psz = (3 * plane + 1) & ~1;
+    constexpr int SLOTS = 3 * PPT * NTHREADS;
+    double *us = smem;                                  // [3][PY][PX]  u = D^-1 r, halo ring (zero outside the domain)
+    double *xs = us + psz;                              // [3][PPT][NTHREADS] x
+    double *ws = xs + SLOTS;                            // [3][PPT][NTHREADS] w = A u
+    double *gs = ws + SLOTS;                            // [3][PPT][NTHREADS] fx, fy, f2
+    double *red = gs + SLOTS;                           // 96 block_sum, 96..99 totals + abort
+    int *hsrc = (int *)(red + 104);                     // import table: offset into g.edges / index into us
+    int *hdst = hsrc + 6 * (tx + ty);
+    int *esrc = hdst + 6 * (tx + ty);                   // export table: index into us / offset into my_edges
+    int *edst = esrc + 6 * (tx + ty);
+    const bool hasN = by > 0, hasS = by < g.gy - 1, hasW = bx > 0, hasE = bx < g.gx - 1;
+    const int edge_stride = 3 * g.maxlen;
+    double *my_edges = g.edges + (size_t)cta * 4 * edge_stride;
+    const int lx = tid % tx, r0 = tid / tx, RPP = NTHREADS / tx;
+    const size_t P = (size_t)w * h;
+
+    for (int i = tid; i < psz; i += NTHREADS) us[i] = 0.0;
+    int nhalo = 0;
+    {   // one list for import and export: entry e of a side = (component c, position pos along the side)
+        const int segNS = 3 * tx, segWE = 3 * ty;
+        for (int e = tid; e < segNS; e += NTHREADS) {
+            const int c = e / tx, pos = e - c * tx;
+            if (hasN) {
+                hsrc[nhalo + e] = ((cta - g.gx) * 4 + 1) * edge_stride + c * g.maxlen + pos; hdst[nhalo + e] = c * plane + pos + 1;
+                esrc[nhalo + e] = c * plane + PX + pos + 1; edst[nhalo + e] = 0 * edge_stride + c * g.maxlen + pos;
+            }
+        }
+        if (hasN) nhalo += segNS;
+        for (int e = tid; e < segNS; e += NTHREADS) {
+            const int c = e / tx, pos = e - c * tx;
+            if (hasS) {
+                hsrc[nhalo + e] = ((cta + g.gx) * 4 + 0) * edge_stride + c * g.maxlen + pos; hdst[nhalo + e] = c * plane + (ty + 1) * PX + pos + 1;
+                esrc[nhalo + e] = c * plane + ty * PX + pos + 1; edst[nhalo + e] = 1 * edge_stride + c * g.maxlen + pos;
+            }
+        }
+        if (hasS) nhalo += segNS;
+        for (int e = tid; e < segWE; e += NTHREADS) {
+            const int c = e / ty, pos = e - c * ty;
+            if (hasW) {
+                hsrc[nhalo + e] = ((cta - 1) * 4 + 3) * edge_stride + c * g.maxlen + pos; hdst[nhalo + e] = c * plane + (pos + 1) * PX;
+                esrc[nhalo + e] = c * plane + (pos + 1) * PX + 1; edst[nhalo + e] = 2 * edge_stride + c * g.maxlen + pos;
+            }
+        }
+        if (hasW) nhalo += segWE;
+        for (int e = tid; e < segWE; e += NTHREADS) {
+            const int c = e / ty, pos = e - c * ty;
+            if (hasE) {
+                hsrc[nhalo + e] = ((cta + 1) * 4 + 2) * edge_stride + c * g.maxlen + pos; hdst[nhalo + e] = c * plane + (pos + 1) * PX + tx + 1;
+                esrc[nhalo + e] = c * plane + (pos + 1) * PX + tx; edst[nhalo + e] = 3 * edge_stride + c * g.maxlen + pos;
+            }
+        }
+        if (hasE) nhalo += segWE;
+    }
+    __syncthreads();                                     // us zeroed before the owners fill it
+
+    double rj[PPT][3], pj[PPT][3], sj[PPT][3];
+    int si[PPT];                                         // index of the pixel in a plane of us | neighbour count << 20 (0: not owned)
+    const int gk0 = (y0 + r0) * w + x0 + lx, gkstep = RPP * w;      // global index of pixel slot j: gk0 + j * gkstep
+#define GK(j) (gk0 + (j) * gkstep)
+#pragma unroll
+    for (int j = 0; j < PPT; j++) {
+        const int ly = j * RPP + r0;
+        si[j] = 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            rj[j][c] = 0.0; pj[j][c] = 0.0; sj[j][c] = 0.0;
+            xs[(c * PPT + j) * NTHREADS + tid] = 0.0; ws[(c * PPT + j) * NTHREADS + tid] = 0.0; gs[(c * PPT + j) * NTHREADS + tid] = 0.0;
+        }
+        if (r0 < RPP && ly < ty) {
+            const int gy_ = y0 + ly, gx_ = x0 + lx;
+            si[j] = ((ly + 1) * PX + lx + 1) | (((gy_ > 0) + (gy_ < h - 1) + (gx_ > 0) + (gx_ < w - 1)) << 20);
+            gs[(0 * PPT + j) * NTHREADS + tid] = a.fx[GK(j)];
+            gs[(1 * PPT + j) * NTHREADS + tid] = a.fy[GK(j)];
+            gs[(2 * PPT + j) * NTHREADS + tid] = a.f2[GK(j)];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double bk = a.b[c * P + GK(j)];
+                rj[j][c] = bk;
+                us[c * plane + (si[j] & 0xFFFFF)] = a.dinv[c * P + GK(j)] * bk;
+            }
+        }
+    }
+    // export pass (all threads, after a __syncthreads that follows the writes of us): round the tile-edge values of
+    // generation gn to its parity in place (owner and neighbour use the same value) and store them
+    auto export_edges = [&](unsigned int gn) {
+        const long long par = (long long)(gn & 1u);
+#pragma unroll
+        for (int e = 0; e < kHaloPerThread; e++) {
+            const int hh = tid + e * NTHREADS;
+            if (hh < nhalo) {
+                const int s = esrc[hh];
+                const double v = __longlong_as_double((__double_as_longlong(us[s]) & ~1ll) | par);
+                us[s] = v;
+                __stcg(my_edges + edst[hh], v);
+            }
+        }
+    };
+    __syncthreads();
+    export_edges(0u);
+    if (tid == 0) red[99] = 0.0;
+
+    unsigned int gen = 0;
+    bool abort = false, pend = false;
+    int it = 0, status = a.maxiter;
+    double stop2 = 0.0, rgam_prev = 0.0, d_prev = 0.0, alpha_prev = 0.0;
+    for (; it < a.maxiter; it++) {
+        // ---- import the neighbours' edge values of generation `it`
+        {
+            const unsigned long long par = (unsigned long long)(it & 1);
+            double hv[kHaloPerThread];
+            const long long t0 = clock64();
+            bool ready;
+            do {
+                ready = true;
+#pragma unroll
+                for (int e = 0; e < kHaloPerThread; e++) {
+                    const int hh = tid + e * NTHREADS;
+                    hv[e] = 0.0;
+                    if (hh < nhalo) {
+                        const unsigned long long bits = ld_relaxed_u64((const unsigned long long *)(g.edges + hsrc[hh]));
+                        ready = ready && (bits & 1ull) == par;
+                        hv[e] = __longlong_as_double((long long)bits);
+                    }
+                }
+                if (!ready && clock64() - t0 > kWatchdogCycles) { *a.sync.error = 1; break; }
+            } while (!ready);
+#ifdef FOTO_PARANOID_FENCES
+            fence_acq_rel_gpu();
+#endif
+#pragma unroll
+            for (int e = 0; e < kHaloPerThread; e++) {
+                const int hh = tid + e * NTHREADS;
+                if (hh < nhalo) us[hdst[hh]] = hv[e];
+            }
+        }
+        __syncthreads();
+        // ---- w = A u, partial r.u, w.u, r.r
+        double acc[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < PPT; j++) {
+            if (si[j]) {
+                const double fx = gs[(0 * PPT + j) * NTHREADS + tid], fy = gs[(1 * PPT + j) * NTHREADS + tid], f2 = gs[(2 * PPT + j) * NTHREADS + tid];
+                double uc[3], nl[3];
+                const double cnt = (double)(si[j] >> 20);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const double *pp = us + c * plane + (si[j] & 0xFFFFF);
+                    uc[c] = pp[0];
+                    nl[c] = cnt * uc[c] - (((pp[-PX] + pp[-1]) + pp[1]) + pp[PX]);
+                }
+                const double gp = fx * uc[0] + fy * uc[1] - f2 * uc[2];
+                const double w0 = a.alpha * nl[0] + fx * gp, w1 = a.alpha * nl[1] + fy * gp, w2 = a.lam * nl[2] - f2 * gp;
+                ws[(0 * PPT + j) * NTHREADS + tid] = w0; ws[(1 * PPT + j) * NTHREADS + tid] = w1; ws[(2 * PPT + j) * NTHREADS + tid] = w2;
+                acc[0] += rj[j][0] * uc[0] + rj[j][1] * uc[1] + rj[j][2] * uc[2];
+                acc[1] += w0 * uc[0] + w1 * uc[1] + w2 * uc[2];
+                acc[2] += rj[j][0] * rj[j][0] + rj[j][1] * rj[j][1] + rj[j][2] * rj[j][2];
+            }
+        }
+        // ---- the one all-reduce; the second half of the previous x update runs in its shadow
+        block_sum<3>(acc, red);
+#ifdef FOTO_PARANOID_FENCES
+        if (tid == 0) grid_arrive<3>(g.slots, gen, acc, true);
+#else
+        if (tid == 0) grid_arrive<3>(g.slots, gen, acc, false);
+#endif
+        if (cta == 0 && tid < 32) grid_root<3, 5>(g.slots, gen, ncta, tid);
+        if (pend) {
+#pragma unroll
+            for (int j = PPT / 2; j < PPT; j++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const int xi = (c * PPT + j) * NTHREADS + tid;
+                    xs[xi] = xs[xi] + alpha_prev * pj[j][c];
+                }
+            pend = false;
+        }
+        if (tid < 3) {
+            const unsigned long long bits = grid_wait(g.slots, gen, tid);
+            red[96 + tid] = __longlong_as_double((long long)bits);
+            if (bits == kAbort) red[99] = 1.0;
+        }
+        __syncthreads();
+        gen++;
+        const double gam = red[96], del = red[97], rho = red[98];
+        abort = red[99] != 0.0;
+        if (abort) break;
+        if (it == 0) {
+            if (rho == 0.0) { status = 0; break; }
+            stop2 = (a.rtol * a.rtol) * rho;                 // sqrt(rho) <= rtol sqrt(rho_0)
+        }
+        if (rho <= stop2) { status = 0; break; }
+        const double beta = gam * rgam_prev;
+        const double dk = del - (beta * beta) * d_prev;      // = delta - beta gamma / alpha_old
+        const double alpha = gam / dk;
+        // ---- p = u + beta p, s = w + beta s, r -= alpha s, u = D^-1 r
+#pragma unroll
+        for (int j = 0; j < PPT; j++) {
+            if (si[j]) {
+                double dv[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) dv[c] = __ldg(a.dinv + c * P + GK(j));
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    double *pu = us + c * plane + (si[j] & 0xFFFFF);
+                    const double sv = sj[j][c] * beta + ws[(c * PPT + j) * NTHREADS + tid];
+                    pj[j][c] = pj[j][c] * beta + pu[0];
+                    sj[j][c] = sv;
+                    const double rv = rj[j][c] - alpha * sv;
+                    rj[j][c] = rv;
+                    pu[0] = dv[c] * rv;
+                }
+            }
+        }
+        __syncthreads();
+        export_edges((unsigned int)it + 1u);
+        // first half of x += alpha p while the edge values travel
+#pragma unroll
+        for (int j = 0; j < PPT / 2; j++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const int xi = (c * PPT + j) * NTHREADS + tid;
+                xs[xi] = xs[xi] + alpha * pj[j][c];
+            }
+        pend = true; alpha_prev = alpha; d_prev = dk;
+        rgam_prev = 1.0 / gam;
+    }
+    if (abort) { if (tid == 0) *a.sync.error = 1; return; }
+#pragma unroll
+    for (int j = 0; j < PPT; j++) {
+        if (si[j]) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                double xv = xs[(c * PPT + j) * NTHREADS + tid];
+                if (pend && j >= PPT / 2) xv = xv + alpha_prev * pj[j][c];
+                a.x[c * P + GK(j)] = xv;
+            }
+        }
+    }
+    if (cta == 0 && tid == 0) { a.out[0] = it; a.out[1] = status; }
+#undef GK
+}
+
+__global__ void k_fill2_u64(unsigned long long *p, int n, unsigned long long v, unsigned long long *q, int m, unsigned long long w)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+    if (i < m) q[i] = w;
+}
+
+constexpr int kThreads = 512, kPPT = 4;
+
+struct Plan { bool ok = false; int gy = 0, gx = 0, maxlen = 0, ncta = 0; size_t smem = 0; };
+
+Plan make_plan(OnchipScratch &d, int device, int h, int w)
+{
+    Plan best;
+    if (!d.num_sms) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return best;
+        d.num_sms = prop.multiProcessorCount; d.smem_optin = prop.sharedMemPerBlockOptin;
+    }
+    long long best_key = -1;
+    for (int gy = 1; gy <= d.num_sms && gy <= h; gy++)
+        for (int gx = 1; gx <= d.num_sms / gy && gx <= w; gx++) {
+            const int ty = (h + gy - 1) / gy, tx = (w + gx - 1) / gx, ty_min = h / gy, tx_min = w / gx;
+            if (tx > kThreads || ty_min < 1 || tx_min < 1) continue;
+            bool fits = true;
+            for (int txx = tx_min; txx <= tx; txx++) if (ty > kPPT * (kThreads / txx)) fits = false;
+            if (!fits) continue;
+            if (6LL * (tx + ty) > (long long)kHaloPerThread * kThreads) continue;
+            const size_t smem = ((((size_t)3 * (ty + 2) * (tx + 2) + 1) & ~size_t(1)) + (size_t)9 * kPPT * kThreads + 104) * 8
+                              + (size_t)24 * (tx + ty) * sizeof(int);
+            if (smem > d.smem_optin) continue;
+            // as cg_fused.cu: tile widths that keep a half-warp inside one row, then short halos and few idle SMs
+            const int straddle = (tx % 16) > 1 ? 1 : 0;
+            const long long key = ((straddle * 100000LL + 6LL * (tx + ty) + 8LL * (d.num_sms - gy * gx)) * 1000) + (999 - tx);
+            if (best_key < 0 || key < best_key) {
+                best_key = key; best.ok = true; best.gy = gy; best.gx = gx; best.ncta = gy * gx;
+                best.maxlen = tx > ty ? tx : ty; best.smem = smem;
+            }
+        }
+    return best;
+}
+
+}  // namespace
+
+bool gn_fused_fits(OnchipScratch &s, int device, int h, int w) { return make_plan(s, device, h, w).ok; }
+
+int launch_gn_fused(cudaStream_t st, const GnArgs &a, int device, OnchipScratch &d)
+{
+    Plan p = make_plan(d, device, a.h, a.w);
+    if (!p.ok) { set_error("image %dx%d does not fit the single-reduction on-chip GN variant", a.h, a.w); return FOTO_ERR_ARG; }
+    const size_t need = (size_t)p.ncta * 4 * 3 * p.maxlen * sizeof(double);
+    if (d.gnf_edges_bytes < need) {
+        if (d.gnf_edges) CUDA_TRY(cudaFree(d.gnf_edges));
+        CUDA_TRY(cudaMalloc((void **)&d.gnf_edges, need));
+        d.gnf_edges_bytes = need;
+    }
+    if (!d.gnf_slots) CUDA_TRY(cudaMalloc((void **)&d.gnf_slots, kSlotWords * sizeof(unsigned long long)));
+    if (!d.gnf_attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute((const void *)gn_fused_kernel<kThreads, kPPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem_optin));
+        d.gnf_attr_set = true;
+    }
+    const int nedge = (int)(need / sizeof(double));
+    k_fill2_u64<<<((nedge > kSlotWords ? nedge : kSlotWords) + 255) / 256, 256, 0, st>>>(d.gnf_slots, kSlotWords, kSentinel, (unsigned long long *)d.gnf_edges, nedge, ~0ull);
+    Geom g;
+    g.gy = p.gy; g.gx = p.gx; g.maxlen = p.maxlen; g.edges = d.gnf_edges; g.slots = d.gnf_slots;
+    void *args[] = {(void *)&a, (void *)&g};
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void *)gn_fused_kernel<kThreads, kPPT>, dim3(p.ncta), dim3(kThreads), args, p.smem, st));
+    return FOTO_OK;
+}
+
+}  // namespace foto

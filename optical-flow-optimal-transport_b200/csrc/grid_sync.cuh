@@ -1,4 +1,4 @@
-// grid_sync.cuh -- grid-wide all-reduce of NV <= 2 doubles for persistent cooperative kernels (one CTA per SM).
+// grid_sync.cuh -- grid-wide all-reduce of NV <= 3 doubles for persistent cooperative kernels (one CTA per SM).
 //
 // Two-hop root gather through L2 (tools/ubench_barrier.cu: 2 450 cycles for 148 CTAs, the floor of L2 signalling;
 // a store -> poll hand-off between two SMs costs 830-1 000 cycles).  Slots hold the raw bits of the partial sums;
@@ -18,7 +18,7 @@ namespace gsync {
 constexpr unsigned long long kSentinel = 0x7FF8DEADBEEF0001ull;
 constexpr unsigned long long kAbort = 0x7FF8DEADBEEF0002ull;
 constexpr unsigned long long kPlainNaN = 0x7FF8000000000000ull;
-constexpr int kNV = 2;                                   // values per all-reduce
+constexpr int kNV = 3;                                   // most values per all-reduce (slot layout stride)
 constexpr int kBcastOff = 3 * kNV * kMaxBlocks;          // slots: [3 gen][kNV][kMaxBlocks] partials, then [3][16] totals
 constexpr int kSlotWords = kBcastOff + 3 * 16;
 constexpr long long kWatchdogCycles = 8000000000ll;
@@ -52,7 +52,7 @@ __device__ __forceinline__ void grid_arrive(unsigned long long *slots, unsigned 
     for (int i = 0; i < NV; i++) st_relaxed_u64(slots + ((gen % 3u) * kNV + i) * kMaxBlocks + blockIdx.x, enc(v[i]));
 }
 
-template <int NV>
+template <int NV, int PER_LANE = 8>
 __device__ __forceinline__ void grid_root(unsigned long long *slots, unsigned int gen, int ncta, int lane)
 {
     const long long t0 = clock64();
@@ -61,15 +61,15 @@ __device__ __forceinline__ void grid_root(unsigned long long *slots, unsigned in
 #pragma unroll
     for (int i = 0; i < NV; i++) tot[i] = 0.0;
     const unsigned long long *cur = slots + (gen % 3u) * kNV * kMaxBlocks;
-    for (int base = 0; base < ncta; base += 256) {
-        unsigned long long v[NV][8];
+    for (int base = 0; base < ncta; base += 32 * PER_LANE) {
+        unsigned long long v[NV][PER_LANE];
         bool ready;
-        do {                                             // all NV x 8 polls of a lane are in flight together
+        do {                                             // all NV x PER_LANE polls of a lane are in flight together
             ready = true;
 #pragma unroll
             for (int i = 0; i < NV; i++)
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
+                for (int k = 0; k < PER_LANE; k++) {
                     const int b = base + k * 32 + lane;
                     v[i][k] = b < ncta ? ld_relaxed_u64(cur + i * kMaxBlocks + b) : 0ull;
                     ready = ready && v[i][k] != kSentinel;
@@ -79,7 +79,7 @@ __device__ __forceinline__ void grid_root(unsigned long long *slots, unsigned in
 #pragma unroll
         for (int i = 0; i < NV; i++)
 #pragma unroll
-            for (int k = 0; k < 8; k++) tot[i] += __longlong_as_double((long long)v[i][k]);
+            for (int k = 0; k < PER_LANE; k++) tot[i] += __longlong_as_double((long long)v[i][k]);
     }
 #ifdef FOTO_PARANOID_FENCES
     fence_acq_rel_gpu();                                 // acquire the partials, release the totals
