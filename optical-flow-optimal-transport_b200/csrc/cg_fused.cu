@@ -45,7 +45,9 @@ struct Geom {
 
 constexpr int kHaloPerThread = 4;
 
-template <int NTHREADS, int NT, int YPT, bool UNIT>
+// XG: x lives in global memory (L2 resident) instead of shared memory: the large variant (576 threads, 9 216 cell
+// slots) for grids such as 480x640x4 whose x slots no longer fit next to r and w
+template <int NTHREADS, int NT, int YPT, bool UNIT, bool XG = false>
 __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
 {
     constexpr int CPT = NT * YPT;
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
     const int psz = (NT * plane + 1) & ~1;
     double *rs = smem;                                  // [NT][PY][PX]  r, halo ring (zero outside the domain)
     double *xs = rs + psz;                              // [CPT][NTHREADS] x
-    double *ws = xs + CPT * NTHREADS;                   // [CPT][NTHREADS] w = A r
+    double *ws = xs + (XG ? 0 : CPT * NTHREADS);        // [CPT][NTHREADS] w = A r
     double *red = ws + CPT * NTHREADS;                  // reduction scratch: 64 block_sum, 64..66 totals, 72..77 profile
     double *dtab = red + 80;                            // diagonal entries for 3..6 neighbours
     int *hsrc = (int *)(dtab + 4);                      // halo import table: offset into g.edges
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
     double pj[CPT], sj[CPT];
     __syncthreads();                                     // rs zeroed before the owners fill it
 #pragma unroll
-    for (int j = 0; j < CPT; j++) { pj[j] = 0.0; sj[j] = 0.0; xs[j * NTHREADS + tid] = 0.0; ws[j * NTHREADS + tid] = 0.0; }
+    for (int j = 0; j < CPT; j++) { pj[j] = 0.0; sj[j] = 0.0; if (!XG) xs[j * NTHREADS + tid] = 0.0; ws[j * NTHREADS + tid] = 0.0; }
 #pragma unroll
     for (int jy = 0; jy < YPT; jy++) {
         if (jy < nval) {
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
             for (int t = 0; t < NT; t++) {
                 const double v = a.b[((size_t)t * Ny + (y0 + ly0 + jy)) * Nx + (x0 + lx)];
                 rs[sb + t * plane + jy * PX] = v;
+                if (XG) a.x[((size_t)t * Ny + (y0 + ly0 + jy)) * Nx + (x0 + lx)] = 0.0;
             }
         }
     }
@@ -167,6 +170,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
     __syncthreads();
     export_edges(0u);
 
+    // x slot j += c * p_j  (slots [j0, j1)); XG: read-modify-write of the owned cell in global memory
+    double *const xg = a.x + ((size_t)(y0 + ly0)) * Nx + (x0 + lx);
+    const size_t Pst = (size_t)Ny * Nx;
+    auto x_update = [&](int j0, int j1, double c) {
+#pragma unroll
+        for (int j = 0; j < CPT; j++) {
+            if (j < j0 || j >= j1) continue;
+            if (XG) {
+                const int t = j / YPT, jy = j - t * YPT;
+                if (jy < nval) { double *px = xg + t * Pst + (size_t)jy * Nx; *px = *px + c * pj[j]; }
+            } else {
+                const int xi = j * NTHREADS + tid;
+                xs[xi] = xs[xi] + c * pj[j];
+            }
+        }
+    };
     unsigned int gen = 0;
     bool abort = false;
     long long tmark = 0;
@@ -265,11 +284,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
 #endif
         if (cta == 0 && tid < 32) grid_root<2>(g.slots, gen, ncta, tid);
         if (pend) {                                      // second half of x += alpha_prev p (first half: after the export)
-#pragma unroll
-            for (int j = CPT / 2; j < CPT; j++) {
-                const int xi = j * NTHREADS + tid;
-                xs[xi] = xs[xi] + alpha_prev * pj[j];
-            }
+            x_update(CPT / 2, CPT, alpha_prev);
             pend = false;
         }
         if (tid < 2) {
@@ -320,11 +335,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
         export_edges((unsigned int)it + 1u);
         lap(3);
         // first half of x += alpha p while the edge values travel
-#pragma unroll
-        for (int j = 0; j < CPT / 2; j++) {
-            const int xi = j * NTHREADS + tid;
-            xs[xi] = xs[xi] + alpha * pj[j];
-        }
+        x_update(0, CPT / 2, alpha);
         lap(4);
         pend = true; alpha_prev = alpha; d_prev = dk;
         rgam_prev = 1.0 / gam;                           // not needed before the next all-reduce has completed
@@ -337,9 +348,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
 #pragma unroll
             for (int t = 0; t < NT; t++) {
                 const int j = t * YPT + jy;
-                double xv = xs[j * NTHREADS + tid];
+                double *px = a.x + ((size_t)t * Ny + (y0 + ly0 + jy)) * Nx + (x0 + lx);
+                double xv = XG ? *px : xs[j * NTHREADS + tid];
                 if (pend && j >= CPT / 2) xv = xv + alpha_prev * pj[j];
-                a.x[((size_t)t * Ny + (y0 + ly0 + jy)) * Nx + (x0 + lx)] = xv;
+                if (!XG || (pend && j >= CPT / 2)) *px = xv;
             }
         }
     }
@@ -354,12 +366,13 @@ __global__ void k_fill2_u64(unsigned long long *p, int n, unsigned long long v, 
     if (i < m) q[i] = w;
 }
 
-constexpr int kThreads = 512;
 // patch shapes: NT time levels x YPT rows per thread (<= 16 cell slots: p and s take 4 registers per slot, the
 // stencil window 6 NT); Nt = 4 is the CLI default and the benchmark configuration
-struct Shape { int nt, ypt; const void *unit, *general; };
-#define FOTO_FUSED_SHAPE(NT, YPT) {NT, YPT, (const void *)cg_fused_kernel<kThreads, NT, YPT, true>, (const void *)cg_fused_kernel<kThreads, NT, YPT, false>}
-const Shape kShapes[] = {FOTO_FUSED_SHAPE(2, 8), FOTO_FUSED_SHAPE(3, 5), FOTO_FUSED_SHAPE(4, 4), FOTO_FUSED_SHAPE(5, 3)};
+struct Shape { int nt, ypt, threads; bool xg; const void *unit, *general; };
+#define FOTO_FUSED_SHAPE(NT, YPT, T, XG) {NT, YPT, T, XG, (const void *)cg_fused_kernel<T, NT, YPT, true, XG>, (const void *)cg_fused_kernel<T, NT, YPT, false, XG>}
+// listed fastest first per Nt: 512 threads with x in shared memory, then (Nt = 4) 576 threads with x in global memory
+const Shape kShapes[] = {FOTO_FUSED_SHAPE(2, 8, 512, false), FOTO_FUSED_SHAPE(3, 5, 512, false), FOTO_FUSED_SHAPE(4, 4, 512, false),
+                         FOTO_FUSED_SHAPE(5, 3, 512, false), FOTO_FUSED_SHAPE(4, 4, 576, true)};
 constexpr int kNumShapes = sizeof(kShapes) / sizeof(kShapes[0]);
 
 struct Plan { bool ok = false; int shape = 0, gy = 0, gx = 0, maxlen = 0, ncta = 0; size_t smem = 0; };
@@ -372,16 +385,16 @@ struct Plan { bool ok = false; int shape = 0, gy = 0, gx = 0, maxlen = 0, ncta =
 Plan make_plan(OnchipScratch &d, int device, int Nt, int Ny, int Nx)
 {
     Plan best;
-    int shape = -1;
-    for (int i = 0; i < kNumShapes; i++) if (kShapes[i].nt == Nt) shape = i;
-    if (shape < 0) return best;
-    const int kNT = Nt, kYPT = kShapes[shape].ypt;
-    best.shape = shape;
     if (!d.num_sms) {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return best;
         d.num_sms = prop.multiProcessorCount; d.smem_optin = prop.sharedMemPerBlockOptin;
     }
+    for (int shape = 0; shape < kNumShapes && !best.ok; shape++) {
+    if (kShapes[shape].nt != Nt) continue;
+    const int kNT = Nt, kYPT = kShapes[shape].ypt, kThreads = kShapes[shape].threads;
+    const int xslots = kShapes[shape].xg ? 1 : 2;       // private shared-memory arrays of kNT*kYPT*kThreads doubles
+    best.shape = shape;
     int force_gy = 0, force_gx = 0;                      // FOTO_ONCHIP_GRID=gy,gx: pin the tile grid (experiments)
     if (const char *e = getenv("FOTO_ONCHIP_GRID")) sscanf(e, "%d,%d", &force_gy, &force_gx);
     long long best_key = -1;
@@ -394,7 +407,7 @@ Plan make_plan(OnchipScratch &d, int device, int Nt, int Ny, int Nx)
             for (int txx = tx_min; txx <= tx; txx++) if (ty > kYPT * (kThreads / txx)) fits = false;
             if (!fits) continue;
             if (2LL * kNT * (tx + ty) > (long long)kHaloPerThread * kThreads) continue;
-            const size_t smem = ((((size_t)kNT * (ty + 2) * (tx + 2) + 1) & ~size_t(1)) + (size_t)2 * kNT * kYPT * kThreads + 80 + 4) * 8
+            const size_t smem = ((((size_t)kNT * (ty + 2) * (tx + 2) + 1) & ~size_t(1)) + (size_t)xslots * kNT * kYPT * kThreads + 80 + 4) * 8
                               + (size_t)8 * kNT * (tx + ty) * sizeof(int);
             if (smem > d.smem_optin) continue;
             const int straddle = (tx % 16) > 1 ? 1 : 0;
@@ -404,6 +417,7 @@ Plan make_plan(OnchipScratch &d, int device, int Nt, int Ny, int Nx)
                 best.maxlen = tx > ty ? tx : ty; best.smem = smem;
             }
         }
+    }
     return best;
 }
 
@@ -436,7 +450,7 @@ int launch_cg_fused(cudaStream_t st, const CgArgs &a, int device, OnchipScratch 
     Geom g;
     g.gy = p.gy; g.gx = p.gx; g.maxlen = p.maxlen; g.edges = d.fused_edges; g.slots = d.fused_slots; g.prof = d.prof;
     void *args[] = {(void *)&a, (void *)&g};
-    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(p.ncta), dim3(kThreads), args, p.smem, st));
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(p.ncta), dim3(kShapes[p.shape].threads), args, p.smem, st));
     return FOTO_OK;
 }
 

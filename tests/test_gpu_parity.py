@@ -634,3 +634,23 @@ def test_cg_kernel_selection(cg_variant):
         run(97, 146, 6)
     assert run(97, 146, 4) == 3
     ctx.close()
+
+
+def test_large_single_reduction_variant_480x640():
+    """480x640x4 (half of the Middlebury sequences) does not fit the 512-thread single-reduction kernel; auto takes its
+    576-thread variant with x in global memory.  Same CG iteration count and phi as the streaming kernel."""
+    import torch
+    h, w, Nt = 480, 640, 4
+    f0, f1 = synth.make_pair(h, w, seed=5)
+    d0 = torch.from_numpy(f0).cuda(); d1 = torch.from_numpy(f1).cuda()
+    res = {}
+    for var in (-1, 0):
+        ctx = foto_b200.Context(0); ctx.set_cg_variant(var)
+        o = [torch.empty(h * w, dtype=torch.float64, device="cuda") for _ in range(3)]
+        info = ctx.solve_dev(d0.data_ptr(), d1.data_ptr(), Nt, w, h, *[t.data_ptr() for t in o], max_it=2, convergence_tol=0.0)
+        res[var] = (ctx.stats()["cg_variant"], list(info["cg_iters"]), torch.stack(o).cpu().numpy())
+        ctx.close()
+    assert res[-1][0] == (1 if os.environ.get("FOTO_NO_FUSED_CG") == "1" else 3)
+    assert res[0][0] == 0
+    assert res[-1][1] == res[0][1]
+    assert relerr(res[-1][2], res[0][2]) < 1e-10

@@ -1,11 +1,12 @@
-"""Sweep FOTO_ONCHIP_GRID tile grids for the on-chip CG kernel on one 388x584x4 pair (us per CG iteration).
-usage: [SWEEP_CONFIGS=0,1] python tools/sweep_grid.py [gy,gx ...]"""
+"""Sweep FOTO_ONCHIP_GRID tile grids for the on-chip CG kernels on one pair (us per CG iteration).
+usage: [SWEEP_SHAPE=388,584] [SWEEP_VARIANT=1|2] [SWEEP_CONFIGS=0,1] python tools/sweep_grid.py [gy,gx ...]   (0,0 = planner's choice)"""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "optical-flow-optimal-transport_b200"))
 import torch, foto_b200
 from foto_b200 import synth
 grids = sys.argv[1:] or ["7,21", "4,37", "12,12", "6,24", "8,18", "9,16", "11,13", "10,14", "5,29", "3,49"]
-h, w, Nt = 388, 584, 4
+h, w = (int(v) for v in os.environ.get("SWEEP_SHAPE", "388,584").split(","))
+Nt = 4
 f0, f1 = synth.make_pair(h, w, seed=0)
 d0 = torch.from_numpy(f0).cuda(); d1 = torch.from_numpy(f1).cuda()
 o = [torch.empty(h * w, dtype=torch.float64, device="cuda") for _ in range(3)]
