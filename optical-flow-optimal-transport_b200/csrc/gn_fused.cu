@@ -292,7 +292,7 @@ __global__ void k_fill2_u64(unsigned long long *p, int n, unsigned long long v, 
     if (i < m) q[i] = w;
 }
 
-constexpr int kThreads = 512, kPPT = 4;
+constexpr int kThreads = 256, kPPT = 8;
 
 struct Plan { bool ok = false; int gy = 0, gx = 0, maxlen = 0, ncta = 0; size_t smem = 0; };
 
