@@ -45,8 +45,9 @@ struct Geom {
 
 constexpr int kHaloPerThread = 4;
 
-// XG: x lives in global memory (L2 resident) instead of shared memory: the large variant (576 threads, 9 216 cell
-// slots) for grids such as 480x640x4 whose x slots no longer fit next to r and w
+// XG: x lives in global memory (L2 resident) instead of shared memory: the large variant (384 threads x 24 cell slots =
+// 9 216; 3 warps per SM sub-partition leave a thread 168 registers) for grids such as 480x640x4 whose x slots no
+// longer fit next to r and w
 template <int NTHREADS, int NT, int YPT, bool UNIT, bool XG = false>
 __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
 {
@@ -371,9 +372,10 @@ __global__ void k_fill2_u64(unsigned long long *p, int n, unsigned long long v, 
 struct Shape { int nt, ypt, threads; bool xg; const void *unit, *general; };
 #define FOTO_FUSED_SHAPE(NT, YPT, T, XG) {NT, YPT, T, XG, (const void *)cg_fused_kernel<T, NT, YPT, true, XG>, (const void *)cg_fused_kernel<T, NT, YPT, false, XG>}
 // listed fastest first per Nt.  Nt = 4: 448 threads (14 warps: 2 % faster than 16 at 388x584x4, 7 168 cell slots), 512
-// threads (8 192), then 576 threads with x in global memory (9 216)
+// threads (8 192), then 384 threads x 24 slots with x in global memory (9 216; 576 threads x 16 slots are capped at 96
+// registers and spill: 10.2 against 7.7 us per iteration at 480x640x4)
 const Shape kShapes[] = {FOTO_FUSED_SHAPE(2, 8, 512, false), FOTO_FUSED_SHAPE(3, 5, 512, false), FOTO_FUSED_SHAPE(4, 4, 448, false),
-                         FOTO_FUSED_SHAPE(4, 4, 512, false), FOTO_FUSED_SHAPE(5, 3, 512, false), FOTO_FUSED_SHAPE(4, 4, 576, true)};
+                         FOTO_FUSED_SHAPE(4, 4, 512, false), FOTO_FUSED_SHAPE(5, 3, 512, false), FOTO_FUSED_SHAPE(4, 6, 384, true)};
 constexpr int kNumShapes = sizeof(kShapes) / sizeof(kShapes[0]);
 
 struct Plan { bool ok = false; int shape = 0, gy = 0, gx = 0, maxlen = 0, ncta = 0; size_t smem = 0; };

@@ -638,7 +638,7 @@ def test_cg_kernel_selection(cg_variant):
 
 def test_large_single_reduction_variant_480x640():
     """480x640x4 (half of the Middlebury sequences) does not fit the 512-thread single-reduction kernel; auto takes its
-    576-thread variant with x in global memory.  Same CG iteration count and phi as the streaming kernel."""
+    large variant (384 threads x 24 cell slots, x in global memory).  Same CG iteration count and phi as the streaming kernel."""
     import torch
     h, w, Nt = 480, 640, 4
     f0, f1 = synth.make_pair(h, w, seed=5)
