@@ -21,8 +21,9 @@
 // barrier or fence: every exported word carries the parity of its generation in the least significant mantissa bit
 // (the owner keeps the same rounded value, so both copies of r agree; the perturbation is one ulp of an edge value
 // per iteration, the size of an ordinary rounding error), and the reader spins on each word until the parity is
-// the one it expects (table-driven export pass after the update, mirror of the import).  One buffer is enough: a CTA overwrites generation g with g+1 only after the all-reduce of
-// iteration g, which every neighbour enters after it has read generation g.  (Measured alternatives: flag + release
+// the one it expects (table-driven export pass after the update, mirror of the import).  One buffer is enough: a CTA
+// overwrites generation g with g+1 only after the all-reduce of iteration g, which every neighbour enters after it
+// has read generation g.  (Measured alternatives: flag + release
 // fence hand-off 2 900 cycles per iteration, as much as the grid barrier it replaces; sentinel reset + triple
 // buffering doubles the stores and costs 3 000 cycles in the reset loop; exporting from registers inside the unrolled
 // update costs the edge warps 1 500 cycles.)  Half of the x update of iteration k covers the L2 hop of the edge
