@@ -209,6 +209,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gn_fused_kernel(GnArgs a, Geom g)
         if (tid == 0) grid_arrive<3>(g.slots, gen, acc, false);
 #endif
         if (cta == 0 && tid < 32) grid_root<3, 5>(g.slots, gen, ncta, tid);
+        // D^-1 of the owned pixels for the update below: requested now, in flight while the all-reduce completes
+        double dv[PPT][3];
+#pragma unroll
+        for (int j = 0; j < PPT; j++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) dv[j][c] = si[j] ? __ldg(a.dinv + c * P + GK(j)) : 0.0;
         if (pend) {
 #pragma unroll
             for (int j = PPT / 2; j < PPT; j++)
@@ -241,9 +247,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gn_fused_kernel(GnArgs a, Geom g)
 #pragma unroll
         for (int j = 0; j < PPT; j++) {
             if (si[j]) {
-                double dv[3];
-#pragma unroll
-                for (int c = 0; c < 3; c++) dv[c] = __ldg(a.dinv + c * P + GK(j));
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     double *pu = us + c * plane + (si[j] & 0xFFFFF);
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gn_fused_kernel(GnArgs a, Geom g)
                     sj[j][c] = sv;
                     const double rv = rj[j][c] - alpha * sv;
                     rj[j][c] = rv;
-                    pu[0] = dv[c] * rv;
+                    pu[0] = dv[j][c] * rv;
                 }
             }
         }
