@@ -376,7 +376,9 @@ struct Shape { int nt, ypt, threads; bool xg; const void *unit, *general; };
 // threads (8 192), then 384 threads x 24 slots with x in global memory (9 216; 576 threads x 16 slots are capped at 96
 // registers and spill: 10.2 against 7.7 us per iteration at 480x640x4)
 const Shape kShapes[] = {FOTO_FUSED_SHAPE(2, 8, 512, false), FOTO_FUSED_SHAPE(3, 5, 512, false), FOTO_FUSED_SHAPE(4, 4, 448, false),
-                         FOTO_FUSED_SHAPE(4, 4, 512, false), FOTO_FUSED_SHAPE(5, 3, 512, false), FOTO_FUSED_SHAPE(4, 6, 384, true)};
+                         FOTO_FUSED_SHAPE(4, 4, 512, false), FOTO_FUSED_SHAPE(5, 3, 512, false), FOTO_FUSED_SHAPE(4, 6, 384, true),
+                         FOTO_FUSED_SHAPE(6, 3, 384, false), FOTO_FUSED_SHAPE(7, 2, 384, false), FOTO_FUSED_SHAPE(8, 2, 384, false),
+                         FOTO_FUSED_SHAPE(16, 1, 256, false)};
 constexpr int kNumShapes = sizeof(kShapes) / sizeof(kShapes[0]);
 
 struct Plan { bool ok = false; int shape = 0, gy = 0, gx = 0, maxlen = 0, ncta = 0; size_t smem = 0; };

@@ -22,7 +22,7 @@ DEGENERATE_TOL = 5e-8
 
 @pytest.fixture(params=["onchip_or_auto", "onchip_textbook", "streaming"], autouse=True)
 def cg_variant(request):
-    """Every test runs three times: auto (single-reduction on-chip CG when Nt <= 5 and the grid fits one tile per
+    """Every test runs three times: auto (single-reduction on-chip CG when Nt <= 8 or 16 and the grid fits one tile per
     SM, else the textbook on-chip kernel, else streaming), the textbook on-chip CG forced where it fits, and the
     streaming CG forced."""
     if request.param == "onchip_textbook":
@@ -612,7 +612,7 @@ def test_gn_onchip_matches_streaming_many_shapes():
 
 def test_cg_kernel_selection(cg_variant):
     """Which Poisson kernel ran (stats.cg_variant): auto takes the single-reduction on-chip kernel for the
-    truncated cg_parity solve at Nt = 2..5 when the grid fits, the textbook on-chip kernel for other Nt and for
+    truncated cg_parity solve at Nt = 2..8 or 16 when the grid fits, the textbook on-chip kernel for other Nt and for
     cg_tight, the streaming kernel when nothing fits; forcing a kernel that does not fit fails loudly."""
     import torch
     ctx = foto_b200.Context(0)
@@ -625,13 +625,15 @@ def test_cg_kernel_selection(cg_variant):
         ctx.solve_dev(d0.data_ptr(), d1.data_ptr(), Nt, w, h, *[t.data_ptr() for t in o], max_it=1, backend=backend)
         return ctx.stats()["cg_variant"]
     assert run(97, 146, 4) == expect[0]
-    assert run(97, 146, 5) == expect[0]                             # patch shapes exist for Nt = 2..5
-    assert run(97, 146, 6) == expect[1]
+    assert run(97, 146, 5) == expect[0]                             # patch shapes exist for Nt = 2..8 and 16
+    assert run(97, 146, 8) == expect[0]
+    assert run(40, 56, 16) == expect[0]
+    assert run(97, 146, 9) == expect[1]
     assert run(97, 146, 4, foto_b200.POISSON_CG_TIGHT) == expect[2]
     assert run(540, 960, 4) == 0                                   # 2 M cells: nothing on-chip fits
     ctx.set_cg_variant(2)
     with pytest.raises(ValueError, match="does not fit"):
-        run(97, 146, 6)
+        run(97, 146, 9)
     assert run(97, 146, 4) == 3
     ctx.close()
 

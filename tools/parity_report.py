@@ -8,7 +8,7 @@ import foto_b200
 from conftest import load_golden, relerr
 
 NAMES = ["foto_24x32", "foto_48x64", "foto_97x146", "foto_37x53_nt5", "foto_40x56_nt16_runsh", "foto_31x29_nt2", "foto_squares32", "foto_388x584"]
-VARIANTS = [("auto (single-reduction on-chip when Nt <= 5)", -1, False), ("on-chip textbook", -1, True), ("streaming", 0, False)]
+VARIANTS = [("auto (single-reduction on-chip, Nt <= 8 or 16)  ", -1, False), ("on-chip textbook", -1, True), ("streaming", 0, False)]
 for name in NAMES:
     g = load_golden(name)
     h, w, Nt = map(int, g["dims"])
