@@ -656,3 +656,25 @@ def test_large_single_reduction_variant_480x640():
     assert res[0][0] == 0
     assert res[-1][1] == res[0][1]
     assert relerr(res[-1][2], res[0][2]) < 1e-10
+
+
+def test_stepA_full_size_true_residual(cg_variant):
+    """388x584x4 (config 1): whichever Poisson kernel runs, the returned phi satisfies scipy's stopping rule with its TRUE
+    residual (the single-reduction kernel carries A p by recurrence, so its recursive residual must not have drifted),
+    and the three kernels agree on the iteration count and on phi to 1e-9."""
+    rng = np.random.default_rng(21)
+    Nt, Ny, Nx = 4, 388, 584
+    N = Nt * Ny * Nx
+    f0, f1 = synth.make_pair(Ny, Nx, seed=0)
+    mu = np.zeros(3 * N); q = 0.01 * rng.standard_normal(3 * N)
+    for n in range(Nt):
+        mu[n * Ny * Nx:(n + 1) * Ny * Nx] = (1 - n / (Nt - 1)) * f0 + n / (Nt - 1) * f1
+    F = foto_b200.rhs(mu, q, f0, f1, 1.0, Nt, Nx, Ny)
+    phi, iters, info = foto_b200.stepA(mu, q, f0, f1, 1.0, 1e-3, Nt, Nx, Ny)
+    assert info == 0 and 100 < iters < 1000
+    L = foto_b200.op_apply("laplacian_st", "N", Nt, Nx, Ny, 1, 1, 1, phi)
+    assert np.linalg.norm((-L + 1e-3 * phi) - F) < 1.0001e-6 * np.linalg.norm(F)
+    foto_b200.set_default_cg_variant(0)
+    os.environ.pop("FOTO_NO_FUSED_CG", None)
+    phi_s, iters_s, _ = foto_b200.stepA(mu, q, f0, f1, 1.0, 1e-3, Nt, Nx, Ny)
+    assert iters == iters_s and relerr(phi, phi_s) < 1e-9
