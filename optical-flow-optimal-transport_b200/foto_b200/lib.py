@@ -97,7 +97,8 @@ def _check(rc):
 
 
 def set_default_cg_variant(variant):
-    """-1 auto (on-chip CG when the grid fits, else streaming), 0 streaming, 1 on-chip."""
+    """-1 auto (fastest kernel that fits: single-reduction on-chip, textbook on-chip, streaming), 0 streaming,
+    1 on-chip with the textbook CG recurrences, 2 on-chip single-reduction.  Applies to the Poisson and the GN solve."""
     _check(lib().foto_set_default_cg_variant(int(variant)))
 
 
