@@ -475,7 +475,7 @@ def test_cg_maxiter_warning_path(capsys, monkeypatch):
 
 # ----------------------------------------------------------------------------- odd shapes (tile decomposition)
 _SHAPES = [(2, 2, 2), (2, 3, 5), (3, 2, 7), (5, 4, 3), (4, 13, 2), (3, 31, 17), (7, 19, 23), (4, 64, 96),
-           (16, 23, 41), (9, 150, 11), (2, 7, 300), (6, 97, 101), (33, 12, 14), (4, 200, 240), (70, 9, 8)]
+           (16, 23, 41), (9, 150, 11), (2, 7, 300), (6, 97, 101), (33, 12, 14), (4, 200, 240), (70, 9, 8), (8, 45, 52)]
 
 
 @pytest.mark.parametrize("Nt,Ny,Nx", _SHAPES)
