@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kThreads) k_stepB(unsigned int N, const double
 // Threads march through t with phi(n-1), phi(n), phi(n+1) in registers: phi is read once from HBM
 // (a flat sweep re-reads it three times at HD size).
 constexpr int kTChunk = 1 << 20;    // one chunk: splitting t across threads (4 planes each) measured slower at 1080x1920x16
-__global__ void __launch_bounds__(kThreads, 3) k_prox_dual(Dims d, const double *__restrict__ phi, double *__restrict__ mu,
+__global__ void __launch_bounds__(kThreads, 4) k_prox_dual(Dims d, const double *__restrict__ phi, double *__restrict__ mu,
                                                          double *__restrict__ q, double r, double inv_r,
                                                          double *__restrict__ partials)
 {
