@@ -75,7 +75,7 @@ typedef struct foto_stats {
     long long rhs_cells, prox_cells;
     long long gn_launches, gn_iterations, gn_pixels;   /* GN persistent PCG kernel       */
     double    gn_ms;
-    int       cg_variant;      /* last Poisson solve: 0 streaming, 1 on-chip, 2 dct_exact, 3 on-chip single-reduction */
+    int       cg_variant;      /* last Poisson solve: 0 streaming, 2 dct_exact, 3 on-chip single-reduction */
     int       reserved;
 } foto_stats;
 
@@ -90,7 +90,7 @@ int  foto_ctx_device(const foto_ctx *ctx);
 int  foto_ctx_set_profiling(foto_ctx *ctx, int on);         /* CUDA-event timing of K1..K4 */
 int  foto_ctx_reset_stats(foto_ctx *ctx);
 int  foto_ctx_get_stats(foto_ctx *ctx, foto_stats *out);
-int  foto_ctx_set_cg_variant(foto_ctx *ctx, int variant);   /* -1 auto, 0 streaming, 1 on-chip (textbook CG), 2 on-chip single-reduction CG */
+int  foto_ctx_set_cg_variant(foto_ctx *ctx, int variant);   /* -1 auto, 0 streaming (textbook CG), 2 on-chip single-reduction CG */
 /* Variant used by the contexts behind the host-buffer API (default -1 = auto; the environment
  * variable FOTO_CG_VARIANT sets the initial value). */
 int  foto_set_default_cg_variant(int variant);

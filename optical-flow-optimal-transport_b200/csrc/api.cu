@@ -178,7 +178,7 @@ extern "C" void foto_ctx_destroy(foto_ctx *c)
     for (auto e : c->watch) if (e) cudaEventDestroy(e);
     cudaFree(c->ws); cudaFree(c->io); cudaFree(c->sync_counter); cudaFree(c->sync_partials);
     cudaFree(c->prox_partials); cudaFree(c->d_res);
-    cg_onchip_release(c->onchip);
+    onchip_release(c->onchip);
     cudaFree(c->dct.base);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -191,7 +191,7 @@ extern "C" int foto_ctx_reset_stats(foto_ctx *c) { if (!c) return FOTO_ERR_ARG; 
 extern "C" int foto_ctx_get_stats(foto_ctx *c, foto_stats *out) { if (!c || !out) return FOTO_ERR_ARG; *out = c->stats; return FOTO_OK; }
 extern "C" int foto_ctx_set_cg_variant(foto_ctx *c, int v)
 {
-    if (!c || v < -1 || v > 2) { set_error("cg variant must be -1, 0, 1 or 2"); return FOTO_ERR_ARG; }
+    if (!c || v < -1 || v > 2 || v == 1) { set_error("cg variant must be -1 (auto), 0 (streaming) or 2 (on-chip single-reduction)"); return FOTO_ERR_ARG; }
     c->cg_variant = v;
     return FOTO_OK;
 }
@@ -216,9 +216,9 @@ extern "C" int foto_ctx_event_elapsed_ms(foto_ctx *c, double *ms)
     return FOTO_OK;
 }
 
-// Debugging aid: cycle counters of CTA 0 of the on-chip CG kernel, accumulated over launches:
-// [0] halo + p update, [1] stencil, [2] barrier 1, [3] r update + edge export, [4] x update,
-// [5] barrier 2 wait, [6] iterations.  enable != 0 (re)starts counting; out may be NULL.
+// Debugging aid: cycle counters of every CTA of the on-chip CG kernel (cg_fused.cu), accumulated over launches:
+// [0] halo import, [1] stencil, [2] all-reduce (+ x/2), [3] p, s, r update + edge export, [4] x/2,
+// [6] iterations.  enable != 0 (re)starts counting; out may be NULL.
 extern "C" int foto_debug_onchip_prof(foto_ctx *c, int enable, long long *out)
 {
     if (!c) return FOTO_ERR_ARG;
@@ -311,20 +311,13 @@ static int run_cg(foto_ctx *c, const Dims &d, const double *F, double *phi, doub
     else { set_error("unknown Poisson back-end %d", backend); return FOTO_ERR_ARG; }
     a.sync.counter = c->sync_counter; a.sync.partials = c->sync_partials; a.sync.error = &c->d_res->error;
     a.out = &c->d_res->cg_iters;
-    // kernel choice: 0 streaming, 1 on-chip (textbook recurrences), 2 on-chip single-reduction, -1 auto = the fastest
-    // that fits (the single-reduction form only for the truncated cg_parity solve it was validated on)
-    const bool fits = cg_onchip_fits(c->onchip, c->device, d.Nt, d.Ny, d.Nx);
+    // kernel choice: 0 streaming (textbook recurrences), 2 on-chip single-reduction, -1 auto = on-chip when the grid
+    // fits (only for the truncated cg_parity solve the single-reduction form was validated on)
     const bool fits_fused = cg_fused_fits(c->onchip, c->device, d.Nt, d.Ny, d.Nx);
-    if (c->cg_variant == 1 && !fits) { set_error("grid %dx%dx%d does not fit the on-chip CG variant", d.Nt, d.Ny, d.Nx); return FOTO_ERR_ARG; }
     if (c->cg_variant == 2 && !fits_fused) { set_error("grid %dx%dx%d does not fit the single-reduction on-chip CG variant", d.Nt, d.Ny, d.Nx); return FOTO_ERR_ARG; }
-    int kind = 0;
-    const char *no_fused = getenv("FOTO_NO_FUSED_CG");      // auto without the single-reduction kernel (tests, A/B runs)
-    const bool auto_fused = c->cg_variant == -1 && fits_fused && backend == FOTO_POISSON_CG_PARITY && !(no_fused && no_fused[0] == '1');
-    if (c->cg_variant == 2 || auto_fused) kind = 3;
-    else if (c->cg_variant != 0 && fits) kind = 1;
+    const int kind = (c->cg_variant == 2 || (c->cg_variant == -1 && fits_fused && backend == FOTO_POISSON_CG_PARITY)) ? 3 : 0;
     prof_begin(c, CAT_CG);
     if (kind == 3) FOTO_TRY(launch_cg_fused(c->stream, a, c->device, c->onchip));
-    else if (kind == 1) FOTO_TRY(launch_cg_onchip(c->stream, a, c->device, c->onchip));
     else FOTO_TRY(launch_cg_stream(c->stream, a, c->cg_grid, c->cg_block));
     prof_end(c);
     c->stats.cg_variant = kind;
@@ -416,16 +409,10 @@ extern "C" int foto_gn_solve_dev(foto_ctx *c, const double *d_f1, const double *
     a.out = &c->d_res->cg_iters;
     launch_gn_coeffs(c->stream, w, h, d_f1, d_f2, alpha, lambda, fx, fy, dinv, b);
     prof_begin(c, CAT_GN);
-    // kernel choice as for the Poisson solve: 0 streaming, 1 on-chip (two all-reduces), 2 on-chip single-reduction,
-    // -1 auto = the fastest that fits
-    const bool gn_fits = gn_onchip_fits(c->onchip, c->device, h, w);
+    // kernel choice as for the Poisson solve: 0 streaming, 2 on-chip single-reduction, -1 auto = on-chip when it fits
     const bool gnf_fits = gn_fused_fits(c->onchip, c->device, h, w);
-    if (c->cg_variant == 1 && !gn_fits) { set_error("image %dx%d does not fit the on-chip GN variant", h, w); return FOTO_ERR_ARG; }
     if (c->cg_variant == 2 && !gnf_fits) { set_error("image %dx%d does not fit the single-reduction on-chip GN variant", h, w); return FOTO_ERR_ARG; }
-    const char *no_fused = getenv("FOTO_NO_FUSED_CG");
-    const bool auto_fused = c->cg_variant == -1 && gnf_fits && !(no_fused && no_fused[0] == '1');
-    if (c->cg_variant == 2 || auto_fused) { FOTO_TRY(launch_gn_fused(c->stream, a, c->device, c->onchip)); c->stats.launches++; }
-    else if (gn_fits && c->cg_variant != 0) { FOTO_TRY(launch_gn_onchip(c->stream, a, c->device, c->onchip)); c->stats.launches++; }
+    if (c->cg_variant == 2 || (c->cg_variant == -1 && gnf_fits)) { FOTO_TRY(launch_gn_fused(c->stream, a, c->device, c->onchip)); c->stats.launches++; }
     else FOTO_TRY(launch_gn_pcg(c->stream, a, c->gn_grid, c->gn_block));
     prof_end(c);
     c->stats.launches += 2; c->stats.gn_launches++;
@@ -454,7 +441,7 @@ static int default_variant()
     if (v == -2) {
         const char *e = getenv("FOTO_CG_VARIANT");
         v = e ? atoi(e) : -1;
-        if (v < -1 || v > 2) v = -1;
+        if (v < -1 || v > 2 || v == 1) v = -1;
         g_default_variant.store(v);
     }
     return v;
@@ -462,7 +449,7 @@ static int default_variant()
 
 extern "C" int foto_set_default_cg_variant(int v)
 {
-    if (v < -1 || v > 2) { set_error("cg variant must be -1, 0, 1 or 2"); return FOTO_ERR_ARG; }
+    if (v < -1 || v > 2 || v == 1) { set_error("cg variant must be -1 (auto), 0 (streaming) or 2 (on-chip single-reduction)"); return FOTO_ERR_ARG; }
     g_default_variant.store(v);
     return FOTO_OK;
 }

@@ -1,9 +1,9 @@
 // cg_fused.cu -- K2a, on-chip resident CG with ONE grid all-reduce per iteration.
 //
-// cg_onchip.cu runs the textbook recurrences (scipy's, benamou_brenier.py:85) and pays two grid all-reduces per
-// iteration (p.Ap, then r.r): 8 800 of its 16 200 cycles per iteration are spent in them, and the all-reduce is at
-// the floor of L2 signalling (tools/ubench_barrier.cu).  This kernel runs the same Krylov iteration in the
-// Chronopoulos-Gear arrangement, which needs one:
+// The textbook recurrences (scipy's, benamou_brenier.py:85; cg_kernels.cu) need two grid all-reduces per iteration
+// (p.Ap, then r.r); an on-chip kernel built that way (round 1, removed) spent 8 800 of its 16 200 cycles per
+// iteration in them, and the all-reduce is at the floor of L2 signalling (grid_sync.cuh).  This kernel runs the same
+// Krylov iteration in the Chronopoulos-Gear arrangement, which needs one:
 //
 //     w = A r,  gamma = r.r,  delta = r.w                      <- one all-reduce of (gamma, delta)
 //     stop if sqrt(gamma) < atol                                  (scipy's test, same place in the sequence)
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
                 const int si = esrc[h];
                 const double v = __longlong_as_double((__double_as_longlong(rs[si]) & ~1ll) | par);
                 rs[si] = v;
-                __stcg(my_edges + edst[h], v);
+                st_relaxed_u64((unsigned long long *)(my_edges + edst[h]), (unsigned long long)__double_as_longlong(v));
             }
         }
     };
@@ -220,11 +220,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
                         hv[e] = __longlong_as_double((long long)bits);
                     }
                 }
-                if (!ready && clock64() - t0 > kWatchdogCycles) { *a.sync.error = 1; break; }
+                if (!ready && clock64() - t0 > kWatchdogCycles) { red[66] = 1.0; break; }     // a neighbour is stuck: abort below
             } while (!ready);
-#ifdef FOTO_PARANOID_FENCES
-            fence_acq_rel_gpu();
-#endif
 #pragma unroll
             for (int e = 0; e < kHaloPerThread; e++) {
                 const int h = tid + e * NTHREADS;
@@ -279,20 +276,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
         lap(1);
         // ---- the one all-reduce; the x update of the previous iteration runs in its shadow
         block_sum<2>(acc, red);
-#ifdef FOTO_PARANOID_FENCES
-        if (tid == 0) grid_arrive<2>(g.slots, gen, acc, true);      // orders this CTA's halo reads before the neighbours' next export
-#else
-        if (tid == 0) grid_arrive<2>(g.slots, gen, acc, false);
-#endif
+        if (tid == 0) grid_arrive<2>(g.slots, gen, acc, red[66] != 0.0);    // an import watchdog of this CTA aborts the whole grid
         if (cta == 0 && tid < 32) grid_root<2>(g.slots, gen, ncta, tid);
         if (pend) {                                      // second half of x += alpha_prev p (first half: after the export)
             x_update(CPT / 2, CPT, alpha_prev);
             pend = false;
         }
-        if (tid < 2) {
-            const unsigned long long bits = grid_wait(g.slots, gen, tid);
-            red[64 + tid] = __longlong_as_double((long long)bits);
-            if (bits == kAbort) red[66] = 1.0;
+        if (tid == 0) {
+            if (!grid_wait<2>(g.slots, gen, red + 64)) red[66] = 1.0;
         }
         __syncthreads();
         gen++;
@@ -431,6 +422,14 @@ Plan make_plan(OnchipScratch &d, int device, int Nt, int Ny, int Nx)
 
 bool cg_fused_fits(OnchipScratch &s, int device, int Nt, int Ny, int Nx) { return make_plan(s, device, Nt, Ny, Nx).ok; }
 
+void onchip_release(OnchipScratch &s)
+{
+    cudaFree(s.prof); cudaFree(s.fused_edges); cudaFree(s.fused_slots); cudaFree(s.gnf_edges); cudaFree(s.gnf_slots);
+    s.prof = nullptr;
+    s.fused_edges = nullptr; s.fused_slots = nullptr; s.fused_edges_bytes = 0;
+    s.gnf_edges = nullptr; s.gnf_slots = nullptr; s.gnf_edges_bytes = 0;
+}
+
 int launch_cg_fused(cudaStream_t st, const CgArgs &a, int device, OnchipScratch &d)
 {
     Plan p = make_plan(d, device, a.Nt, a.Ny, a.Nx);
@@ -451,8 +450,8 @@ int launch_cg_fused(cudaStream_t st, const CgArgs &a, int device, OnchipScratch 
         d.fused_attr_set = true;
     }
     const int nedge = (int)(need / sizeof(double));
-    // slots <- sentinel; edge words <- odd parity ("generation 0 not yet written")
-    k_fill2_u64<<<((nedge > kSlotWords ? nedge : kSlotWords) + 255) / 256, 256, 0, st>>>(d.fused_slots, kSlotWords, kSentinel, (unsigned long long *)d.fused_edges, nedge, ~0ull);
+    // all-reduce slots and edge words <- odd parity ("generation 0 not yet written")
+    k_fill2_u64<<<((nedge > kSlotWords ? nedge : kSlotWords) + 255) / 256, 256, 0, st>>>(d.fused_slots, kSlotWords, kSlotInit, (unsigned long long *)d.fused_edges, nedge, ~0ull);
     Geom g;
     g.gy = p.gy; g.gx = p.gx; g.maxlen = p.maxlen; g.edges = d.fused_edges; g.slots = d.fused_slots; g.prof = d.prof;
     void *args[] = {(void *)&a, (void *)&g};

@@ -59,29 +59,20 @@ struct CgArgs {
 int cg_stream_config(int device, int *grid, int *block);
 int launch_cg_stream(cudaStream_t st, const CgArgs &a, int grid, int block);
 
-// on-chip resident variant (state in shared memory/registers, one tile per SM); cg_onchip.cu
-struct OnchipScratch {          // owned by the context
+// scratch of the on-chip resident kernels (state in shared memory/registers, one tile per SM), owned by the context
+struct OnchipScratch {
     int num_sms = 0;
     size_t smem_optin = 0;
-    double *edges = nullptr; size_t edges_bytes = 0;
-    unsigned long long *slots = nullptr;
-    long long *prof = nullptr;  // 8 cycle counters (debugging aid, see foto_debug_onchip_prof)
-    bool attr_set = false;
-    int forced_cfg = -1;        // FOTO_ONCHIP_CONFIG: pin one (threads, cells/thread) configuration
+    long long *prof = nullptr;  // 8 cycle counters per CTA (debugging aid, see foto_debug_onchip_prof)
     double *fused_edges = nullptr; size_t fused_edges_bytes = 0;   // cg_fused.cu
     unsigned long long *fused_slots = nullptr;
     bool fused_attr_set = false;
     double *gnf_edges = nullptr; size_t gnf_edges_bytes = 0;    // gn_fused.cu
     unsigned long long *gnf_slots = nullptr;
     bool gnf_attr_set = false;
-    double *gn_edges = nullptr; size_t gn_edges_bytes = 0;      // gn_onchip.cu
-    unsigned long long *gn_slots = nullptr;
-    bool gn_attr_set = false;
 };
-bool cg_onchip_fits(OnchipScratch &s, int device, int Nt, int Ny, int Nx);
-int launch_cg_onchip(cudaStream_t st, const CgArgs &a, int device, OnchipScratch &s);
-void cg_onchip_release(OnchipScratch &s);
-// on-chip resident, one grid all-reduce per iteration (Chronopoulos-Gear arrangement, Nt = 4); cg_fused.cu
+void onchip_release(OnchipScratch &s);
+// on-chip resident, one grid all-reduce per iteration (Chronopoulos-Gear arrangement); cg_fused.cu
 bool cg_fused_fits(OnchipScratch &s, int device, int Nt, int Ny, int Nx);
 int launch_cg_fused(cudaStream_t st, const CgArgs &a, int device, OnchipScratch &s);
 
@@ -117,10 +108,7 @@ struct GnArgs {
 };
 int gn_pcg_config(int device, int *grid, int *block);
 int launch_gn_pcg(cudaStream_t st, const GnArgs &a, int grid, int block);
-// on-chip resident variant (gn_onchip.cu): uses fx, fy, f2, dinv, b, x, out, sync.error of GnArgs only
-bool gn_onchip_fits(OnchipScratch &s, int device, int h, int w);
-int launch_gn_onchip(cudaStream_t st, const GnArgs &a, int device, OnchipScratch &s);
-// on-chip resident, one grid all-reduce per iteration (gn_fused.cu)
+// on-chip resident, one grid all-reduce per iteration (gn_fused.cu): uses fx, fy, f2, dinv, b, x, out, sync.error only
 bool gn_fused_fits(OnchipScratch &s, int device, int h, int w);
 int launch_gn_fused(cudaStream_t st, const GnArgs &a, int device, OnchipScratch &s);
 

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gn_fused_kernel(GnArgs a, Geom g)
                 const int s = esrc[hh];
                 const double v = __longlong_as_double((__double_as_longlong(us[s]) & ~1ll) | par);
                 us[s] = v;
-                __stcg(my_edges + edst[hh], v);
+                st_relaxed_u64((unsigned long long *)(my_edges + edst[hh]), (unsigned long long)__double_as_longlong(v));
             }
         }
     };
@@ -167,11 +167,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gn_fused_kernel(GnArgs a, Geom g)
                         hv[e] = __longlong_as_double((long long)bits);
                     }
                 }
-                if (!ready && clock64() - t0 > kWatchdogCycles) { *a.sync.error = 1; break; }
+                if (!ready && clock64() - t0 > kWatchdogCycles) { red[99] = 1.0; break; }      // a neighbour is stuck: abort below
             } while (!ready);
-#ifdef FOTO_PARANOID_FENCES
-            fence_acq_rel_gpu();
-#endif
 #pragma unroll
             for (int e = 0; e < kHaloPerThread; e++) {
                 const int hh = tid + e * NTHREADS;
@@ -203,11 +200,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gn_fused_kernel(GnArgs a, Geom g)
         }
         // ---- the one all-reduce; the second half of the previous x update runs in its shadow
         block_sum<3>(acc, red);
-#ifdef FOTO_PARANOID_FENCES
-        if (tid == 0) grid_arrive<3>(g.slots, gen, acc, true);
-#else
-        if (tid == 0) grid_arrive<3>(g.slots, gen, acc, false);
-#endif
+        if (tid == 0) grid_arrive<3>(g.slots, gen, acc, red[99] != 0.0);
         if (cta == 0 && tid < 32) grid_root<3, 5>(g.slots, gen, ncta, tid);
         // D^-1 of the owned pixels for the update below: requested now, in flight while the all-reduce completes
         double dv[PPT][3];
@@ -225,10 +218,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gn_fused_kernel(GnArgs a, Geom g)
                 }
             pend = false;
         }
-        if (tid < 3) {
-            const unsigned long long bits = grid_wait(g.slots, gen, tid);
-            red[96 + tid] = __longlong_as_double((long long)bits);
-            if (bits == kAbort) red[99] = 1.0;
+        if (tid == 0) {
+            if (!grid_wait<3>(g.slots, gen, red + 96)) red[99] = 1.0;
         }
         __syncthreads();
         gen++;
@@ -350,7 +341,7 @@ int launch_gn_fused(cudaStream_t st, const GnArgs &a, int device, OnchipScratch 
         d.gnf_attr_set = true;
     }
     const int nedge = (int)(need / sizeof(double));
-    k_fill2_u64<<<((nedge > kSlotWords ? nedge : kSlotWords) + 255) / 256, 256, 0, st>>>(d.gnf_slots, kSlotWords, kSentinel, (unsigned long long *)d.gnf_edges, nedge, ~0ull);
+    k_fill2_u64<<<((nedge > kSlotWords ? nedge : kSlotWords) + 255) / 256, 256, 0, st>>>(d.gnf_slots, kSlotWords, kSlotInit, (unsigned long long *)d.gnf_edges, nedge, ~0ull);
     Geom g;
     g.gy = p.gy; g.gx = p.gx; g.maxlen = p.maxlen; g.edges = d.gnf_edges; g.slots = d.gnf_slots;
     void *args[] = {(void *)&a, (void *)&g};

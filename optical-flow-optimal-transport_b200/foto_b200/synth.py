@@ -3,11 +3,9 @@
 The generator is the one SURVEY.md §8(d) fixes for configs 1-5: a Gaussian-filtered
 uniform-noise texture, frame 2 = cubic-spline sub-pixel shift of frame 1, both on
 the 8-bit lattice k/255 that the reference's image loader produces
-(reference utils.py:39-42).  The brightness perturbation follows the recipe of the
-reference's dataset tool (bin/create_lum_dataset.py:23-56: two random rectangles and
-two random discs of +-0.25 brightness, clipped, re-quantised) but is vectorised and
-driven by a numpy Generator, so it is a recipe-alike, not a byte-for-byte clone of
-that tool's `random` stream.
+(reference utils.py:39-42).  The brightness perturbation and the joint normalisation are
+byte-for-byte restatements of the reference's dataset tools (bin/create_lum_dataset.py,
+bin/normalize_image.py); tests/golden/lum.npz holds outputs of the tools themselves.
 """
 import numpy as np
 
@@ -38,35 +36,42 @@ def make_pair(h, w, seed=0, shift=(0.4, 0.7), sigma=3.0):
     return np.ascontiguousarray(f0).ravel(), np.ascontiguousarray(f1).ravel()
 
 
+def _trunc8(a):
+    """`np.uint8(255*np.clip(f, 0, 1))` then the loader's `/255`: what a PNG round trip through the reference's
+    dataset tools does to an image (truncation, not rounding; bin/create_lum_dataset.py:57, utils.py:39-42)."""
+    return np.uint8(255 * np.clip(a, 0, 1)).astype(np.float64) / 255
+
+
 def perturb_brightness(f, h, w, seed):
-    """Two rectangles + two discs of uniform(-0.25, 0.25) brightness, clipped, 8-bit."""
-    rng = np.random.default_rng(seed)
+    """Byte-for-byte restatement of the reference's illumination tool (bin/create_lum_dataset.py:23-57) for
+    `random.seed(seed)`: two random rectangles, then two random discs, each adding uniform(-0.25, 0.25), then
+    clip and truncate to 8 bits.  The `random` calls are made in the tool's order (L_x, L_y, r_x, r_y, v per
+    rectangle; R, c_x, c_y, v per disc); the pixel loops are array slices adding the same value once per pixel,
+    so the float results are the tool's.  Checked against the tool itself in tests/golden/lum.npz."""
+    import random
+    rnd = random.Random(seed)                            # same Mersenne stream as random.seed(seed)
     img = np.array(f, dtype=np.float64).reshape(h, w).copy()
-    yy, xx = np.mgrid[0:h, 0:w]
     for _ in range(2):
-        lx = int(rng.integers(10, w)); ly = int(rng.integers(10, h))
-        cx = int(rng.integers(lx // 2, w - lx // 2 + 1))
-        cy = int(rng.integers(ly // 2, h - ly // 2 + 1))
-        val = rng.uniform(-0.25, 0.25)
-        y0, y1 = max(0, cy - ly // 2), min(h, cy + ly // 2)
-        x0, x1 = max(0, cx - lx // 2), min(w, cx + lx // 2)
-        img[y0:y1, x0:x1] += val
+        L_x = rnd.randint(10, w - 1); L_y = rnd.randint(10, h - 1)
+        r_x = rnd.randint(int(L_x / 2), int(w - L_x / 2)); r_y = rnd.randint(int(L_y / 2), int(h - L_y / 2))
+        v = rnd.uniform(-0.25, 0.25)
+        img[int(r_y - L_y / 2):int(r_y + L_y / 2), int(r_x - L_x / 2):int(r_x + L_x / 2)] += v
+    jj, ii = np.mgrid[0:h, 0:w]
     for _ in range(2):
-        rad = int(rng.integers(10, min(w, h) + 1)) / 2.0
-        cx = int(rng.integers(int(rad), int(w - rad) + 1))
-        cy = int(rng.integers(int(rad), int(h - rad) + 1))
-        val = rng.uniform(-0.25, 0.25)
-        img[(xx - cx) ** 2 + (yy - cy) ** 2 < rad ** 2] += val
-    return _quantise(img).ravel()
+        R = rnd.randint(10, min(w, h)) / 2
+        c_x = rnd.randint(int(R), int(w - R)); c_y = rnd.randint(int(R), int(h - R))
+        v = rnd.uniform(-0.25, 0.25)
+        img[(ii - c_x) ** 2 + (jj - c_y) ** 2 < R ** 2] += v
+    return _trunc8(img).ravel()
 
 
 def normalize_pair(f0, f1):
-    """Joint mass / peak normalisation of the reference's bin/normalize_image.py:20-26: each frame is
-    scaled to unit mass, then both are divided by the larger peak and re-quantised to 8 bits."""
-    a = np.asarray(f0, dtype=np.float64) / np.sum(f0)
-    b = np.asarray(f1, dtype=np.float64) / np.sum(f1)
-    scale = max(a.max(), b.max())
-    return _quantise(a / scale), _quantise(b / scale)
+    """Joint mass / peak normalisation of the reference's bin/normalize_image.py:20-29: each frame is scaled to
+    unit mass, both are divided by the larger peak, clipped and truncated to 8 bits (what the saved PNGs hold)."""
+    a = np.asarray(f0, dtype=np.float64); b = np.asarray(f1, dtype=np.float64)
+    a = a / np.sum(a); b = b / np.sum(b)
+    scale = max(np.max(a), np.max(b))
+    return _trunc8(a / scale), _trunc8(b / scale)
 
 
 def two_squares(n=32):
@@ -90,3 +95,21 @@ def make_batch(n_pairs, h=388, w=584, base_seed=0):
             f1 = perturb_brightness(f1, h, w, seed=12345 + p)
         pairs.append((f0, f1))
     return pairs
+
+
+CONFIG3_PARAMS = dict(r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=100)     # reference CLI defaults (main.py:38-42)
+
+
+def config3_pairs(sequences=None, perturbations=range(8)):
+    """BASELINE.json config 3: 8 Middlebury-shape sequences x 8 perturbations = 64 pairs.
+    Sequence s: texture seed s, sub-pixel shift (0.4 + 0.05 s, 0.7 - 0.05 s); perturbation p = 0 is the clean
+    pair, p > 0 applies the reference's illumination tool (perturb_brightness, random.seed(12345 + p)) to frame 2.
+    Returns [(name, h, w, f0, f1)] in sequence-major order; the one definition tools, tests and goldens share."""
+    out = []
+    for s, (name, (h, w)) in enumerate(MIDDLEBURY_SHAPES.items()):
+        if sequences is not None and s not in sequences and name not in sequences:
+            continue
+        f0, f1 = make_pair(h, w, seed=s, shift=(0.4 + 0.05 * s, 0.7 - 0.05 * s))
+        for p in perturbations:
+            out.append((f"{name}/{p}", h, w, f0, f1 if p == 0 else perturb_brightness(f1, h, w, seed=12345 + p)))
+    return out

@@ -20,19 +20,12 @@ DEGENERATE = {"foto_31x29_nt2", "foto_squares32"}     # see tests/test_oracle_go
 DEGENERATE_TOL = 5e-8
 
 
-@pytest.fixture(params=["onchip_or_auto", "onchip_textbook", "streaming"], autouse=True)
+@pytest.fixture(params=["onchip_or_auto", "streaming"], autouse=True)
 def cg_variant(request):
-    """Every test runs three times: auto (single-reduction on-chip CG when Nt <= 8 or 16 and the grid fits one tile per
-    SM, else the textbook on-chip kernel, else streaming), the textbook on-chip CG forced where it fits, and the
-    streaming CG forced."""
-    if request.param == "onchip_textbook":
-        foto_b200.set_default_cg_variant(-1)
-        os.environ["FOTO_NO_FUSED_CG"] = "1"
-    else:
-        os.environ.pop("FOTO_NO_FUSED_CG", None)
-        foto_b200.set_default_cg_variant(0 if request.param == "streaming" else -1)
+    """Every test runs twice: auto (single-reduction on-chip CG when Nt <= 8 or 16 and the grid fits one tile per
+    SM, else streaming) and the streaming CG (textbook recurrences) forced."""
+    foto_b200.set_default_cg_variant(0 if request.param == "streaming" else -1)
     yield request.param
-    os.environ.pop("FOTO_NO_FUSED_CG", None)
     foto_b200.set_default_cg_variant(-1)
 
 
@@ -585,7 +578,7 @@ def test_gn_large_image_streaming_property():
     y, b = foto_b200.gn_system(f0, f1, w, h, 0.1, 0.2, np.concatenate([u, v, m]))
     assert np.linalg.norm(y - b) < 2e-10 * np.linalg.norm(b)
     ctx = foto_b200.Context(0)
-    ctx.set_cg_variant(1)
+    ctx.set_cg_variant(2)
     out = [np.empty(h * w) for _ in range(3)]
     with pytest.raises(ValueError, match="does not fit"):
         ctx.gn_solve_host(f0, f1, w, h, 0.1, 0.2, *out)
@@ -612,11 +605,11 @@ def test_gn_onchip_matches_streaming_many_shapes():
 
 def test_cg_kernel_selection(cg_variant):
     """Which Poisson kernel ran (stats.cg_variant): auto takes the single-reduction on-chip kernel for the
-    truncated cg_parity solve at Nt = 2..8 or 16 when the grid fits, the textbook on-chip kernel for other Nt and for
-    cg_tight, the streaming kernel when nothing fits; forcing a kernel that does not fit fails loudly."""
+    truncated cg_parity solve at Nt = 2..8 or 16 when the grid fits, the streaming kernel for other Nt, for cg_tight
+    and when the grid does not fit; forcing a kernel that does not fit (or the removed variant 1) fails loudly."""
     import torch
     ctx = foto_b200.Context(0)
-    expect = {"onchip_or_auto": (3, 1, 1), "onchip_textbook": (1, 1, 1), "streaming": (0, 0, 0)}[cg_variant]
+    expect = {"onchip_or_auto": (3, 0, 0), "streaming": (0, 0, 0)}[cg_variant]
     ctx.set_cg_variant(0 if cg_variant == "streaming" else -1)
     def run(h, w, Nt, backend=foto_b200.POISSON_CG_PARITY):
         f0, f1 = synth.make_pair(h, w, seed=2)
@@ -635,6 +628,8 @@ def test_cg_kernel_selection(cg_variant):
     with pytest.raises(ValueError, match="does not fit"):
         run(97, 146, 9)
     assert run(97, 146, 4) == 3
+    with pytest.raises(ValueError, match="cg variant"):
+        ctx.set_cg_variant(1)
     ctx.close()
 
 
@@ -652,7 +647,7 @@ def test_large_single_reduction_variant_480x640():
         info = ctx.solve_dev(d0.data_ptr(), d1.data_ptr(), Nt, w, h, *[t.data_ptr() for t in o], max_it=2, convergence_tol=0.0)
         res[var] = (ctx.stats()["cg_variant"], list(info["cg_iters"]), torch.stack(o).cpu().numpy())
         ctx.close()
-    assert res[-1][0] == (1 if os.environ.get("FOTO_NO_FUSED_CG") == "1" else 3)
+    assert res[-1][0] == 3
     assert res[0][0] == 0
     assert res[-1][1] == res[0][1]
     assert relerr(res[-1][2], res[0][2]) < 1e-10
@@ -661,7 +656,7 @@ def test_large_single_reduction_variant_480x640():
 def test_stepA_full_size_true_residual(cg_variant):
     """388x584x4 (config 1): whichever Poisson kernel runs, the returned phi satisfies scipy's stopping rule with its TRUE
     residual (the single-reduction kernel carries A p by recurrence, so its recursive residual must not have drifted),
-    and the three kernels agree on the iteration count and on phi to 1e-9."""
+    and the two kernels agree on the iteration count and on phi to 1e-9."""
     rng = np.random.default_rng(21)
     Nt, Ny, Nx = 4, 388, 584
     N = Nt * Ny * Nx
@@ -675,6 +670,5 @@ def test_stepA_full_size_true_residual(cg_variant):
     L = foto_b200.op_apply("laplacian_st", "N", Nt, Nx, Ny, 1, 1, 1, phi)
     assert np.linalg.norm((-L + 1e-3 * phi) - F) < 1.0001e-6 * np.linalg.norm(F)
     foto_b200.set_default_cg_variant(0)
-    os.environ.pop("FOTO_NO_FUSED_CG", None)
     phi_s, iters_s, _ = foto_b200.stepA(mu, q, f0, f1, 1.0, 1e-3, Nt, Nx, Ny)
     assert iters == iters_s and relerr(phi, phi_s) < 1e-9

@@ -18,9 +18,7 @@ d0 = torch.from_numpy(f0).cuda(); d1 = torch.from_numpy(f1).cuda()
 du, dv, dm = (torch.empty(P, dtype=torch.float64, device="cuda") for _ in range(3))
 kw = dict(r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=100)
 res = {}
-for variant, cfg in ((0, None), (2, None), (1, 0), (1, 1)):
-    if cfg is not None:
-        os.environ["FOTO_ONCHIP_CONFIG"] = str(cfg)
+for variant, cfg in ((0, None), (2, None)):
     ctx = foto_b200.Context(0)
     ctx.set_cg_variant(variant)
     ctx.solve_dev(d0.data_ptr(), d1.data_ptr(), Nt, w, h, du.data_ptr(), dv.data_ptr(), dm.data_ptr(), **kw)
@@ -37,9 +35,7 @@ for variant, cfg in ((0, None), (2, None), (1, 0), (1, 1)):
         c = ctx.onchip_prof(False)
         c = c[c[:, 6] > 0].astype(float)
         it = c[:, 6:7]
-        names = ["halo+p update", "stencil", "barrier1", "r update+edges", "x update(+gather)", "barrier2 wait"]
-        if variant == 2:
-            names = ["halo import (spin)", "stencil", "all-reduce (+x/2)", "p,s,r update+export", "x/2 (hop)", "-"]
+        names = ["halo import (spin)", "stencil", "all-reduce (+x/2)", "p,s,r update+export", "x/2 (hop)", "-"]
         per = c[:, :6] / it
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         np.savetxt(os.path.join(ROOT, "gpurun_out", f"phase_cycles_variant{variant}_cfg{cfg}.csv"), per, fmt="%.0f", delimiter=",")

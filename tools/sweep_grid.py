@@ -1,5 +1,5 @@
-"""Sweep FOTO_ONCHIP_GRID tile grids for the on-chip CG kernels on one pair (us per CG iteration).
-usage: [SWEEP_SHAPE=388,584] [SWEEP_VARIANT=1|2] [SWEEP_CONFIGS=0,1] python tools/sweep_grid.py [gy,gx ...]   (0,0 = planner's choice)"""
+"""Sweep FOTO_ONCHIP_GRID tile grids for the on-chip CG kernel on one pair (us per CG iteration).
+usage: [SWEEP_SHAPE=388,584] python tools/sweep_grid.py [gy,gx ...]   (0,0 = planner's choice)"""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "optical-flow-optimal-transport_b200"))
 import torch, foto_b200
@@ -11,9 +11,8 @@ f0, f1 = synth.make_pair(h, w, seed=0)
 d0 = torch.from_numpy(f0).cuda(); d1 = torch.from_numpy(f1).cuda()
 o = [torch.empty(h * w, dtype=torch.float64, device="cuda") for _ in range(3)]
 kw = dict(r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=100)
-for cfg in os.environ.get("SWEEP_CONFIGS", "0").split(","):
-    os.environ["FOTO_ONCHIP_CONFIG"] = cfg
-    ctx = foto_b200.Context(0); ctx.set_cg_variant(int(os.environ.get("SWEEP_VARIANT", "1")))
+for cfg in ["0"]:
+    ctx = foto_b200.Context(0); ctx.set_cg_variant(2)
     for g in grids:
         os.environ["FOTO_ONCHIP_GRID"] = g
         try:
