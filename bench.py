@@ -2,28 +2,29 @@
 """bench.py -- FOTO frame-pairs/s at 388x584 on N B200s (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
-    python bench.py --impl reference [--gpus N] [--steps K] ...    # CPU reference arm (oracle port)
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # CPU reference arm (oracle port, full solves)
 
-One "step" = one pass of the hot path over one batch: every rank solves `--pairs-per-gpu`
-synthetic 388x584 pairs (Nt=4, r=1, tol=0.1, eps=1e-3, max_it=100: the reference CLI defaults,
-main.py:38-42) with benamou_brenier.solve semantics (cg_parity Poisson back-end).  Pairs are
-independent, so ranks never communicate on the data path (weak scaling); the only collectives
-are the barriers and the max-over-ranks of the device time.
+One "step" = one pass of the hot path over one batch of N x `--pairs-per-gpu` synthetic 388x584 pairs (Nt=4, r=1,
+tol=0.1, eps=1e-3, max_it=100: the reference CLI defaults, main.py:38-42) with benamou_brenier.solve semantics
+(cg_parity Poisson back-end).  Pairs are independent, so ranks never communicate on the data path (weak scaling);
+every rank holds the whole batch and draws pair indices from one shared queue (foto_b200.shard.WorkQueue, an atomic
+counter in the process group's store), because outer and CG iteration counts are data dependent; the only
+collectives are the barriers, the max-over-ranks of the device time and the gather of per-rank statistics.
 
-  value  : pairs/s, inputs resident in HBM, timed with CUDA events on the library's stream
-  e2e    : pairs/s through the host-buffer C-ABI call the shim modules make (pinned host
-           inputs, H2D + solve + D2H inside the timed region, wall clock)
-  roofline: the persistent CG kernel (K2a), algorithmic bytes 88 B/cell/CG-iteration
-            over its CUDA-event time, against MEASURED_PEAKS.json
-  cpu_baseline: the C oracle (a port of the reference's algorithm) on a bounded sample
+  value   : pairs/s, inputs resident in HBM, timed with CUDA events on the library's stream (max over ranks)
+  e2e     : pairs/s through the host-buffer C-ABI call the shim modules make (pinned host inputs, H2D + solve + D2H
+            inside the timed region, wall clock)
+  roofline: the HBM statement the path supports: the streaming kernels K1 / K2a / K3 on a 1080x1920x16 volume
+            (3.2 GB, 25x the L2), algorithmic bytes of SURVEY.md section 8(d) over CUDA-event time, worst kernel
+            as the headline.  The dominant kernel of the config-1 solve (cg_fused_kernel, state resident in shared
+            memory and registers) is not HBM bound; `onchip` reports it against its own limits.
+  cpu_baseline: the C oracle (a port of the reference's algorithm), one full solve on one core
 """
 import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import threading
 import time
 
@@ -39,12 +40,11 @@ H, W, NT = 388, 584, 4
 PARAMS = dict(r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=100)
 P = H * W
 N = NT * P
-CG_KERNEL_NAMES = {0: "cg_stream_kernel", 1: "cg_onchip_kernel", 3: "cg_fused_kernel"}   # foto_stats.cg_variant
+CG_KERNEL_NAMES = {0: "cg_stream_kernel", 3: "cg_fused_kernel"}   # foto_stats.cg_variant
 CG_BYTES_PER_CELL_ITER = 88      # 11 fp64 words per cell per CG iteration
 RHS_BYTES_PER_CELL = 56
 PROX_BYTES_PER_CELL = 80
-CPU_SAMPLE_OUTER = 2             # outer iterations timed on the CPU (of the 9 the config needs)
-EXPECTED_OUTER = 9               # measured with the reference on pair 0
+REFERENCE_BUDGET_S = 300.0       # wall budget of the timed steps of --impl reference (full solves, ~65 s per step)
 
 
 def pair_seed(rank, i):
@@ -61,51 +61,53 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clocks / throttle reasons of the GPUs in use during the timed region (B200_PROFILING.md's clocks line),
+    read through NVML from one thread of rank 0 (a `nvidia-smi -lms` process per rank stalls every rank's launches
+    while it holds the driver lock)."""
 
-    def __init__(self, index):
-        self.index = index
-        self.proc = None
-        self.path = None
+    def __init__(self, indices, period_s=0.2):
+        self.indices, self.period = list(indices), period_s
+        self.rows, self._stop, self._thr, self.err = [], threading.Event(), None, None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            hs = [nv.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+            mx = [nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM) for h in hs]
+            while not self._stop.is_set():
+                for h, m in zip(hs, mx):
+                    self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), m, nv.nvmlDeviceGetPowerUsage(h) / 1e3,
+                                      nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons")
+                                      else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+                self._stop.wait(self.period)
+        except Exception as e:          # sampling is best effort
+            self.err = f"{type(e).__name__}: {e}"
 
     def __enter__(self):
-        try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        if self.indices:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
         return self
 
     def __exit__(self, *a):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except Exception:
-                self.proc.kill()
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=5)
 
     def summary(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        try:
-            rows = [l.strip().split(", ") for l in open(self.path) if l.strip()]
-            sm = [float(r[0]) for r in rows]
-            out["sm_mhz"] = statistics.median(sm)
-            out["sm_max_mhz"] = float(rows[0][1])
-            out["power_w_max"] = max(float(r[2]) for r in rows)
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            out["reasons"] = [n for i, n in enumerate(names) if any(r[3 + i].strip() == "Active" for r in rows)]
-            out["samples"] = len(rows)
-        except Exception as e:      # sampling is best effort
-            out["error"] = str(e)
-        finally:
-            if self.path and os.path.exists(self.path):
-                os.unlink(self.path)
+        if self.rows:
+            out["sm_mhz"] = float(statistics.median(r[0] for r in self.rows))
+            out["sm_min_mhz"] = float(min(r[0] for r in self.rows))
+            out["sm_max_mhz"] = float(max(r[1] for r in self.rows))
+            out["power_w_max"] = max(r[2] for r in self.rows)
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            out["reasons"] = [n for n, b in bits.items() if any(r[3] & b for r in self.rows)]
+            out["samples"] = len(self.rows)
+            out["gpus_sampled"] = len(self.indices)
+        if self.err:
+            out["error"] = self.err
         return out
 
 
@@ -114,33 +116,30 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------ CPU oracle legs
-def _cpu_sample_worker(arg):
-    """One bounded CPU sample: the first n_outer outer iterations of one pair."""
-    seed, n_outer = arg if isinstance(arg, tuple) else (arg, CPU_SAMPLE_OUTER)
+def _cpu_full_solve(seed_index):
+    """One complete reference solve on the CPU: the ALG2 loop to its stopping rule + flow extraction."""
     import oracle
     from foto_b200 import synth
-    f0, f1 = synth.make_pair(H, W, seed=pair_seed(0, seed))
+    f0, f1 = synth.make_pair(H, W, seed=pair_seed(0, seed_index))
     t0 = time.perf_counter()
-    kw = dict(PARAMS)
-    kw["max_it"] = n_outer
-    kw["convergence_tol"] = 0.0
-    _, _, _, info = oracle.solve(f0, f1, NT, W, H, return_info=True, **kw)
+    _, _, _, info = oracle.solve(f0, f1, NT, W, H, return_info=True, **PARAMS)
     return time.perf_counter() - t0, int(info["n_outer"])
 
 
 def cpu_baseline_single():
     import oracle
     oracle.build()
-    dt, outer = _cpu_sample_worker(0)
-    pairs_per_s = (outer / EXPECTED_OUTER) / dt
-    return {"value": pairs_per_s, "unit": "pairs/s", "cores": 1, "kind": "port",
-            "sample": f"C oracle (oracle/foto_oracle.c), first {outer} of {EXPECTED_OUTER} outer iterations of pair 0 "
-                      f"in {dt:.1f} s, scaled by {EXPECTED_OUTER}/{outer}; the unmodified Python reference needs "
-                      f"259.7 s/pair on one core (BASELINE.md section 2)"}
+    dt, outer = _cpu_full_solve(0)
+    return {"value": 1.0 / dt, "unit": "pairs/s", "cores": 1, "kind": "port",
+            "sample": f"C oracle (oracle/foto_oracle.c), one full solve of pair 0 ({outer} outer iterations + flow "
+                      f"extraction) in {dt:.1f} s on one core; the unmodified Python reference needs 259.7 s/pair on "
+                      f"one core (BASELINE.md section 2)"}
 
 
 def run_reference(args):
-    """--impl reference: the oracle port on all host cores, one pair per process per step."""
+    """--impl reference: the oracle port on all host cores, one FULL solve of one pair per process per step
+    (nothing extrapolated).  A step costs about a minute, so the number of timed steps is bounded by
+    REFERENCE_BUDGET_S and reported in `steps`."""
     rank, _, world = dist_env()
     if rank != 0:
         return
@@ -149,25 +148,30 @@ def run_reference(args):
     oracle.build()
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     cores = min(avail, 64)           # the path is DRAM-bound on the host: more processes only add contention
-    times = []
+    times, outers = [], []
     with mp.get_context("fork").Pool(cores) as pool:
-        for step in range(args.warmup + args.steps):
+        t_begin = time.perf_counter()
+        for step in range(max(args.steps, 1)):
             t0 = time.perf_counter()
-            res = pool.map(_cpu_sample_worker, [(i, 1) for i in range(cores)])   # 1 of ~9 outer iterations each
+            res = pool.map(_cpu_full_solve, list(range(cores)))
             dt = time.perf_counter() - t0
-            if step >= args.warmup:
-                times.append(dt)
-            outer = res[0][1]
+            times.append(dt); outers += [o for _, o in res]
+            if time.perf_counter() - t_begin + dt > REFERENCE_BUDGET_S:
+                break
+    steps = len(times)
     total = sum(times)
-    value = args.steps * cores * (outer / EXPECTED_OUTER) / total
-    sample = (f"per step, {cores} processes (of {avail} usable cores) each run the first {outer} of {EXPECTED_OUTER} outer iterations of one "
-              f"388x584 pair with the C oracle (port of the reference's algorithm; the reference itself is pure "
-              f"Python and cannot travel to the GPU box); pairs/s scaled by {EXPECTED_OUTER}/{outer}")
+    value = steps * cores / total
+    sample = (f"{steps} timed step(s) (of {args.steps} requested; wall budget {REFERENCE_BUDGET_S:.0f} s, no warm-up: nothing to warm "
+              f"on the CPU); per step {cores} processes (of {avail} usable cores) each run one FULL solve of one 388x584 pair "
+              f"with the C oracle (port of the reference's algorithm: ALG2 loop to its stopping rule, mean {statistics.mean(outers):.2f} "
+              f"outer iterations, + flow extraction); the reference itself is pure Python (259.7 s/pair on one core) and cannot "
+              f"travel to the GPU box")
     line = {"impl": "reference", "metric": "FOTO frame-pairs/s at 388x584", "value": value, "unit": "pairs/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "n_gpus": args.gpus, "steps": steps, "steps_requested": args.steps, "warmup": 0,
+            "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "foto_388x584_nt4_cli_defaults", "poisson_backend": "cg_parity"},
+            "config": {"workload": "foto_388x584_nt4_cli_defaults", "poisson_backend": "cg_parity", "pairs_per_step": cores,
+                       "params": PARAMS},
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -178,7 +182,7 @@ def run_reference(args):
 def run_b200(args):
     import torch
     import foto_b200
-    from foto_b200 import synth
+    from foto_b200 import shard, synth
     rank, local_rank, world = dist_env()
     if world > 1:
         import torch.distributed as dist
@@ -190,79 +194,91 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     B = args.pairs_per_gpu
+    NB = world * B                       # pairs per step, whole job
     ctx = foto_b200.Context(local_rank)
     if args.cg_variant is not None:
         ctx.set_cg_variant(args.cg_variant)
 
-    # synthetic pairs, distinct per rank; resident in HBM before the timed region
-    pairs = [synth.make_pair(H, W, seed=pair_seed(rank, i)) for i in range(B)]
-    h0 = torch.empty((B, P), dtype=torch.float64).pin_memory()
-    h1 = torch.empty((B, P), dtype=torch.float64).pin_memory()
+    # the whole batch is resident on every GPU (pinned host copy + HBM copy) before any timed region
+    pairs = [synth.make_pair(H, W, seed=pair_seed(r, i)) for r in range(world) for i in range(B)]
+    h0 = torch.empty((NB, P), dtype=torch.float64).pin_memory()
+    h1 = torch.empty((NB, P), dtype=torch.float64).pin_memory()
     for i, (a, b) in enumerate(pairs):
         h0[i] = torch.from_numpy(a); h1[i] = torch.from_numpy(b)
     d0, d1 = h0.to(dev), h1.to(dev)
-    du, dv, dm = (torch.empty((B, P), dtype=torch.float64, device=dev) for _ in range(3))
-    hu, hv, hm = (torch.empty((B, P), dtype=torch.float64).pin_memory() for _ in range(3))
+    du, dv, dm = (torch.empty((NB, P), dtype=torch.float64, device=dev) for _ in range(3))
+    hu, hv, hm = (torch.empty((NB, P), dtype=torch.float64).pin_memory() for _ in range(3))
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     torch.cuda.synchronize()
-
-    from foto_b200 import shard
 
     def barrier():
         shard.barrier()
         torch.cuda.synchronize()
 
-    outer_counts = []
-
-    def step_device():
-        for i in range(B):
-            info = ctx.solve_dev(d0[i].data_ptr(), d1[i].data_ptr(), NT, W, H, du[i].data_ptr(), dv[i].data_ptr(),
-                                 dm[i].data_ptr(), **PARAMS)
-            outer_counts.append(info["n_outer"])
-
-    def step_host():
-        n0, n1, nu, nv, nm = (t.numpy() for t in (h0, h1, hu, hv, hm))
-        for i in range(B):
-            ctx.solve_host(n0[i], n1[i], NT, W, H, nu[i], nv[i], nm[i], **PARAMS)
-
     def l2_flush():
         flush.zero_()
-        torch.cuda.synchronize()
+
+    qn = [0]
+
+    def run_steps(n_steps, solve_one):
+        """n_steps passes over the batch, pairs drawn from the shared queue; L2 flushed after every B solves of this rank."""
+        qn[0] += 1
+        q = shard.WorkQueue(f"bench{qn[0]}", n_steps * NB)
+        done = 0
+        while True:
+            i = q.next()
+            if i is None:
+                break
+            solve_one(i % NB)
+            done += 1
+            if done % B == 0:
+                l2_flush()
+        return done
+
+    log = {"pairs": 0, "outer": 0, "cg": 0}
+
+    def solve_dev(i):
+        info = ctx.solve_dev(d0[i].data_ptr(), d1[i].data_ptr(), NT, W, H, du[i].data_ptr(), dv[i].data_ptr(), dm[i].data_ptr(), **PARAMS)
+        log["pairs"] += 1; log["outer"] += int(info["n_outer"]); log["cg"] += int(info["cg_iters"].sum())
+
+    n0, n1, nu, nv, nm = (t.numpy() for t in (h0, h1, hu, hv, hm))
+
+    def solve_host(i):
+        ctx.solve_host(n0[i], n1[i], NT, W, H, nu[i], nv[i], nm[i], **PARAMS)
 
     # ---- device-resident throughput ("value")
-    for _ in range(args.warmup):
-        step_device(); l2_flush()
+    run_steps(args.warmup, solve_dev)
+    torch.cuda.synchronize()
+    log.update(pairs=0, outer=0, cg=0)
     ctx.set_profiling(True); ctx.reset_stats()
     barrier()
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(range(world) if rank == 0 else []) as clk:
         ctx.event_record(0)
-        for _ in range(args.steps):
-            step_device(); l2_flush()
+        run_steps(args.steps, solve_dev)
         ctx.event_record(1)
-        dev_ms = ctx.event_elapsed_ms()
+        dev_ms_rank = ctx.event_elapsed_ms()
     barrier()
     stats = ctx.stats()
     clocks = clk.summary()
     ctx.set_profiling(False)
 
     # ---- end to end through the host-buffer C ABI ("e2e")
-    for _ in range(min(args.warmup, 2)):
-        step_host()
+    run_steps(min(args.warmup, 1), solve_host)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host(); l2_flush()
+    e2e_pairs = run_steps(args.steps, solve_host)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
 
-    # ---- GN (config 2) on the same pairs, device resident -- auxiliary figure
+    # ---- GN (config 2) on this rank's pairs, device resident -- auxiliary figure
+    mine = list(range(rank * B, rank * B + B))
     gn_iters = []
     for _ in range(2):
-        ctx.gn_solve_dev(d0[0].data_ptr(), d1[0].data_ptr(), W, H, 0.1, 0.2, du[0].data_ptr(), dv[0].data_ptr(), dm[0].data_ptr())
+        ctx.gn_solve_dev(d0[mine[0]].data_ptr(), d1[mine[0]].data_ptr(), W, H, 0.1, 0.2, du[0].data_ptr(), dv[0].data_ptr(), dm[0].data_ptr())
     barrier()
     ctx.event_record(0)
-    for i in range(B):
+    for i in mine:
         gn_iters.append(ctx.gn_solve_dev(d0[i].data_ptr(), d1[i].data_ptr(), W, H, 0.1, 0.2, du[i].data_ptr(),
                                          dv[i].data_ptr(), dm[i].data_ptr())["iters"])
     ctx.event_record(1)
@@ -270,35 +286,59 @@ def run_b200(args):
     barrier()
 
     # ---- opt-in exact Poisson back-end (dct_exact): same pairs, device resident -- auxiliary figure
-    for i in range(B):
+    for i in mine:
         ctx.solve_dev(d0[i].data_ptr(), d1[i].data_ptr(), NT, W, H, du[i].data_ptr(), dv[i].data_ptr(), dm[i].data_ptr(),
                       backend=foto_b200.POISSON_DCT_EXACT, **PARAMS)
     barrier()
     ctx.event_record(0)
-    for i in range(B):
+    for i in mine:
         ctx.solve_dev(d0[i].data_ptr(), d1[i].data_ptr(), NT, W, H, du[i].data_ptr(), dv[i].data_ptr(), dm[i].data_ptr(),
                       backend=foto_b200.POISSON_DCT_EXACT, **PARAMS)
     ctx.event_record(1)
     dct_ms = ctx.event_elapsed_ms()
     barrier()
 
-    # device times: max over ranks (no-op without a process group)
-    dev_ms, e2e_ms, gn_ms, dct_ms = shard.max_over_ranks([dev_ms, e2e_s * 1e3, gn_ms, dct_ms], device=dev)
+    # device times: max over ranks (no-op without a process group); per-rank record for the scaling analysis
+    dev_ms, e2e_ms, gn_ms, dct_ms = shard.max_over_ranks([dev_ms_rank, e2e_s * 1e3, gn_ms, dct_ms], device=dev)
+    per_rank = shard.gather_objects({"rank": rank, "ms": dev_ms_rank, "pairs": log["pairs"], "outer_iterations": log["outer"],
+                                     "cg_iterations": log["cg"], "cg_ms": stats["cg_ms"], "e2e_ms": e2e_s * 1e3, "e2e_pairs": e2e_pairs,
+                                     "launches": int(stats["launches"])})
 
     if rank == 0:
         peak, peak_src = peaks()
-        total_pairs = world * B * args.steps
+        total_pairs = NB * args.steps
+        assert sum(r["pairs"] for r in per_rank) == total_pairs, per_rank
         value = total_pairs / (dev_ms / 1e3)
-        cg_bytes = CG_BYTES_PER_CELL_ITER * stats["cg_cells"]
+        tot_cg = sum(r["cg_iterations"] for r in per_rank); tot_outer = sum(r["outer_iterations"] for r in per_rank)
         cg_s = stats["cg_ms"] / 1e3
-        achieved = cg_bytes / cg_s / 1e9 if cg_s > 0 else 0.0
-        traffic, traffic_src = None, None            # DRAM bytes per launch from the committed ncu --set full capture
+        us_iter = 1e3 * stats["cg_ms"] / max(stats["cg_iterations"], 1)
+        kname = CG_KERNEL_NAMES.get(stats["cg_variant"], "cg_stream_kernel")
+        traffic = {}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            t = json.load(open(tpath)).get(CG_KERNEL_NAMES.get(stats["cg_variant"], "cg_stream_kernel"))
-            if t:
-                traffic, traffic_src = t["dram_bytes_per_launch"], t["source"]
-        per_launch_iters = stats["cg_iterations"] / max(stats["cg_launches"], 1)
+            traffic = json.load(open(tpath))
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        onchip = {
+            "kernel": kname, "share_of_step": stats["cg_ms"] / dev_ms_rank, "avg_launch_ms": stats["cg_ms"] / max(stats["cg_launches"], 1),
+            "cg_iterations_per_launch": stats["cg_iterations"] / max(stats["cg_launches"], 1),
+            "us_per_cg_iteration": us_iter, "cycles_per_cg_iteration": us_iter * sm_mhz,
+            "algorithmic_88B_rate_GBs": CG_BYTES_PER_CELL_ITER * stats["cg_cells"] / cg_s / 1e9 if cg_s > 0 else 0.0,
+            "algorithmic_88B_rate_note": "algorithmic bytes of SURVEY.md 8(d) over kernel time; the state (x, r, p, s, w) never leaves "
+                                         "shared memory / registers, so this is NOT HBM traffic and is not compared with the HBM peak",
+        }
+        t = traffic.get(kname)
+        if t:
+            onchip["dram_bytes_per_launch_ncu"] = t["dram_bytes_per_launch"]
+            onchip["ncu_source"] = t["source"]
+            if "lsu_shared_wavefronts_per_iteration_per_sm" in t:
+                wf = t["lsu_shared_wavefronts_per_iteration_per_sm"]; ar = t["allreduce_floor_cycles"]
+                onchip["bounds"] = {
+                    "shared_memory_pipe": {"wavefronts_per_iteration_per_sm": wf, "peak_wavefronts_per_clk": 1,
+                                           "frac_of_iteration": wf / onchip["cycles_per_cg_iteration"]},
+                    "grid_allreduce_floor_cycles": ar,
+                    "frac_of_serial_floor": (wf + ar) / onchip["cycles_per_cg_iteration"],
+                    "note": "an iteration cannot be shorter than its shared-memory wavefronts (1 per clock per SM) plus one grid "
+                            "all-reduce (two L2 traversals, tools/ubench_allreduce2.cu); frac_of_serial_floor = that floor / measured cycles"}
         line = {
             "metric": "FOTO frame-pairs/s at 388x584", "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -306,48 +346,54 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "foto_388x584_nt4_cli_defaults", "pairs_per_gpu_per_step": B,
                        "params": PARAMS, "poisson_backend": "cg_parity",
-                       "cg_variant": {0: "streaming", 1: "on-chip (textbook recurrences, 2 all-reduces/iteration)",
+                       "cg_variant": {0: "streaming (textbook recurrences)",
                                       3: "on-chip single-reduction (Chronopoulos-Gear arrangement)"}.get(stats["cg_variant"], "?"),
-                       "l2": "512 MB device memset between steps (working set 87 MB/pair < 126 MB L2)",
-                       "outer_iterations_per_pair": statistics.mean(outer_counts) if outer_counts else None},
-            "outer_iters_per_s": world * stats["cg_launches"] / (dev_ms / 1e3),
-            "cg_iters_per_s": world * stats["cg_iterations"] / (dev_ms / 1e3),
+                       "sharding": "by pair, one shared work queue over all ranks (no data-path collective)",
+                       "l2": "512 MB device memset after every pairs_per_gpu solves (working set 87 MB/pair < 126 MB L2)",
+                       "outer_iterations_per_pair": tot_outer / max(total_pairs, 1)},
+            "outer_iters_per_s": tot_outer / (dev_ms / 1e3),
+            "cg_iters_per_s": tot_cg / (dev_ms / 1e3),
             "e2e": {"value": total_pairs / (e2e_ms / 1e3), "unit": "pairs/s",
-                    "h2d_bytes_per_step": B * 2 * P * 8, "d2h_bytes_per_step": B * 3 * P * 8,
-                    "timing": "wall clock around foto_solve_host calls, pinned host buffers"},
-            "gpu_launches": int(stats["launches"]),
+                    "h2d_bytes_per_step": NB * 2 * P * 8, "d2h_bytes_per_step": NB * 3 * P * 8,
+                    "timing": "wall clock around foto_solve_host calls, pinned host buffers, max over ranks"},
+            "gpu_launches": sum(r["launches"] for r in per_rank),
             "clocks": clocks,
-            "roofline": {"kernel": CG_KERNEL_NAMES.get(stats["cg_variant"], "cg_stream_kernel"),
-                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": CG_BYTES_PER_CELL_ITER * N * per_launch_iters,
-                         "avg_launch_ms": stats["cg_ms"] / max(stats["cg_launches"], 1),
-                         "cg_iterations_per_launch": per_launch_iters,
-                         "us_per_cg_iteration": 1e3 * stats["cg_ms"] / max(stats["cg_iterations"], 1),
-                         "share_of_step": stats["cg_ms"] / dev_ms,
-                         "note": "working set (4 CG vectors = 29 MB) is L2/SM resident at this size, so the "
-                                 "algorithmic-bytes rate is not bounded by HBM; see DESIGN.md",
-                         "other_kernels": {
-                             "rhs_K1_GBs": RHS_BYTES_PER_CELL * stats["rhs_cells"] / max(stats["rhs_ms"], 1e-9) / 1e6,
-                             "prox_dual_K3_GBs": PROX_BYTES_PER_CELL * stats["prox_cells"] / max(stats["prox_ms"], 1e-9) / 1e6}},
+            "per_rank": per_rank,
+            "onchip": onchip,
             "aux": {"gn_solves_per_s": world * B / (gn_ms / 1e3), "gn_pcg_iterations": statistics.mean(gn_iters),
                     "gn_config": "GN 388x584 alpha=0.1 lambda=0.2, PCG rtol 1e-13 (config 2)",
                     "foto_dct_exact_pairs_per_s": world * B / (dct_ms / 1e3),
                     "foto_dct_exact_note": "opt-in exact Poisson back-end; differs from the reference's truncated CG by "
                                            "~5e-7 relative (parity-gated against the tight oracle only)"},
         }
-        if world == 1 and not args.no_hd:
-            line["roofline_streaming_hd"] = hd_roofline(ctx, torch, dev, peak)
+        if not args.no_hd:
+            hd = hd_roofline(ctx, torch, dev, peak)
+            worst = min(("K1_rhs", "K2a_cg_stream", "K3_prox_dual"), key=lambda k: hd[k]["frac"])
+            tk = {"K1_rhs": "k_rhs", "K2a_cg_stream": "cg_stream_kernel", "K3_prox_dual": hd["K3_prox_dual"]["kernel"]}[worst]
+            tr = traffic.get(tk, {})
+            line["roofline"] = {"bound": "hbm", "kernel": tk, "achieved": hd[worst]["achieved"], "peak": peak, "unit": "GB/s",
+                                "frac": hd[worst]["achieved"] / peak,
+                                "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
+                                "peak_source": peak_src,
+                                "algorithmic_bytes_per_launch": hd[worst]["algorithmic_bytes_per_launch"],
+                                "avg_launch_ms": hd[worst]["ms"],
+                                "what": "worst of the three streaming kernels of one ALG2 iteration on a 1080x1920x16 volume "
+                                        "(3.2 GB working set, 25x the L2); the config-1 solve itself is SM-resident, see `onchip`",
+                                "streaming_hd": hd}
+        else:
+            line["roofline"] = {"bound": "hbm", "kernel": None, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                                "traffic": None, "note": "--no-hd: HBM-bound streaming kernels not measured in this run"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single()
         print(json.dumps(line), file=_OUT, flush=True)
+    barrier()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
 
 
 def hd_roofline(ctx, torch, dev, peak):
-    """HBM-bound evidence: one outer ALG2 iteration on a 1080x1920x16 grid (3.2 GB working set, 25x the
+    """HBM-bound evidence: outer ALG2 iterations on a 1080x1920x16 grid (3.2 GB working set, 25x the
     L2), streaming CG kernel, CUDA events per kernel.  Not part of `value`."""
     from foto_b200 import synth
     h, w, Nt = 1080, 1920, 16
@@ -356,19 +402,26 @@ def hd_roofline(ctx, torch, dev, peak):
     a = torch.from_numpy(f0).to(dev); b = torch.from_numpy(f1).to(dev)
     o = [torch.empty(P_, dtype=torch.float64, device=dev) for _ in range(3)]
     kw = dict(r=1.0, convergence_tol=0.0, reg_epsilon=1e-3, max_it=1)
+    ctx.set_cg_variant(0)
     ctx.solve_dev(a.data_ptr(), b.data_ptr(), Nt, w, h, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), **kw)
     ctx.set_profiling(True); ctx.reset_stats()
     ctx.solve_dev(a.data_ptr(), b.data_ptr(), Nt, w, h, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), **kw)
     st = ctx.stats(); ctx.set_profiling(False)
+    ctx.set_cg_variant(-1)
     gbs = lambda bytes_per_cell, cells, ms: bytes_per_cell * cells / max(ms, 1e-9) / 1e6
     k1 = gbs(RHS_BYTES_PER_CELL, st["rhs_cells"], st["rhs_ms"])
     k2 = gbs(CG_BYTES_PER_CELL_ITER, st["cg_cells"], st["cg_ms"])
     k3 = gbs(PROX_BYTES_PER_CELL, st["prox_cells"], st["prox_ms"])
+    k3_name = "k_prox_dual" if os.environ.get("FOTO_K3") == "legacy" else "k_prox_dual_tma"
     return {"grid": [Nt, h, w], "cells": N_, "working_set_GB": 12 * N_ * 8 / 1e9, "peak": peak, "unit": "GB/s",
-            "K1_rhs": {"achieved": k1, "frac": k1 / peak, "ms": st["rhs_ms"]},
-            "K2a_cg_stream": {"achieved": k2, "frac": k2 / peak, "us_per_cg_iteration": 1e3 * st["cg_ms"] / max(st["cg_iterations"], 1),
-                              "cg_iterations": st["cg_iterations"], "bytes_per_cell_iteration": CG_BYTES_PER_CELL_ITER},
-            "K3_prox_dual": {"achieved": k3, "frac": k3 / peak, "ms": st["prox_ms"]}}
+            "K1_rhs": {"kernel": "k_rhs", "achieved": k1, "frac": k1 / peak, "ms": st["rhs_ms"],
+                       "algorithmic_bytes_per_launch": RHS_BYTES_PER_CELL * N_},
+            "K2a_cg_stream": {"kernel": "cg_stream_kernel", "achieved": k2, "frac": k2 / peak, "ms": st["cg_ms"],
+                              "us_per_cg_iteration": 1e3 * st["cg_ms"] / max(st["cg_iterations"], 1),
+                              "cg_iterations": st["cg_iterations"], "bytes_per_cell_iteration": CG_BYTES_PER_CELL_ITER,
+                              "algorithmic_bytes_per_launch": CG_BYTES_PER_CELL_ITER * N_ * st["cg_iterations"]},
+            "K3_prox_dual": {"kernel": k3_name, "achieved": k3, "frac": k3 / peak, "ms": st["prox_ms"],
+                             "algorithmic_bytes_per_launch": PROX_BYTES_PER_CELL * N_}}
 
 
 _OUT = sys.stdout
@@ -381,7 +434,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=4)
-    ap.add_argument("--cg-variant", type=int, default=None, help="-1 auto, 0 streaming, 1 on-chip textbook, 2 on-chip single-reduction")
+    ap.add_argument("--cg-variant", type=int, default=None, help="-1 auto, 0 streaming, 2 on-chip single-reduction")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hd", action="store_true", help="skip the 1080x1920x16 streaming-roofline measurement")
     args = ap.parse_args()

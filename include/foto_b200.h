@@ -48,7 +48,7 @@ extern "C" {
 #define FOTO_OP_GRAD            3   /* operators.py:160-169   P  -> 2P */
 #define FOTO_OP_DIV             4   /* operators.py:182-191   2P -> P  */
 #define FOTO_OP_GRAD_FORWARD    5   /* operators.py:171-180   P  -> 2P */
-/* 1-D builder ids for foto_op_apply_1d (operators.py:5-110) */
+/* 1-D builder ids for foto_tri_coeffs (operators.py:5-110) */
 #define FOTO_1D_FORWARD_WEIRD   0
 #define FOTO_1D_BACKWARD_WEIRD  1
 #define FOTO_1D_CENTRAL_WEIRD   2
@@ -192,6 +192,29 @@ int  foto_pack_flo(const double *u, const double *v, int n, float *out_2n);
 /* utils.EE / utils.AE (utils.py:294-338): out6 = [sum EE, sum EE^2, #EE<=50, sum AE, sum AE^2, #AE not NaN];
  * mean = sum/count, stddev = sqrt(sumsq/count - mean^2). */
 int  foto_flow_metrics(const double *u, const double *v, const double *uGT, const double *vGT, int n, double *out6);
+
+/* ---- device-resident ingest / egress: consume the solver's device outputs ------------
+ * All pointers are device pointers; work is enqueued on the context's stream (no host synchronisation except
+ * where a host result is returned). */
+/* utils.openGrayscaleImage's conversion (utils.py:39-42): 8-bit grey -> float64 k/255, bit-identical to numpy */
+int  foto_ingest_u8_dev(foto_ctx *ctx, const unsigned char *d_u8, int n, double *d_out);
+/* utils.saveFlo payload (utils.py:285-292): d_out_2n = n interleaved float32 (u, v) pairs */
+int  foto_pack_flo_dev(foto_ctx *ctx, const double *d_u, const double *d_v, int n, float *d_out_2n);
+/* utils.EE / utils.AE sums as foto_flow_metrics; d_out6: 6 doubles on the device */
+int  foto_flow_metrics_dev(foto_ctx *ctx, const double *d_u, const double *d_v, const double *d_uGT, const double *d_vGT,
+                           int n, double *d_out6);
+/* utils.apply_opticalflow (utils.py:186-248) on device buffers; d_m may be NULL; then IE's sum of squares
+ * (utils.py:340-354) against d_IGT when d_ie_sumsq != NULL: *d_ie_sumsq = sum (255 out - 255 IGT)^2 */
+int  foto_warp_dev(foto_ctx *ctx, const double *d_f1, const double *d_u, const double *d_v, int w, int h,
+                   const double *d_m_or_null, double *d_out, const double *d_IGT_or_null, double *d_ie_sumsq_or_null);
+
+/* Batched ingest + solve + .flo egress: n_pairs pairs of 8-bit grey frames (what the image files hold; 8x less
+ * H2D traffic than float64) through pinned staging, benamou_brenier.solve on the device, results returned as the
+ * float32 .flo payload (n_pairs * 2P floats) and, optionally, m (n_pairs * P doubles, may be NULL).  Sharded over
+ * devices like foto_solve_batch. */
+int  foto_solve_batch_u8(int n_pairs, const unsigned char *f0s, const unsigned char *f1s, int Nt, int Nx, int Ny,
+                         double r, double tol, double eps, int max_it, int poisson_backend,
+                         const int *device_ids, int n_dev, float *flo_payloads, double *ms_or_null, int *n_outer);
 
 /* Many independent pairs of one shape, sharded over devices by a work queue (one host thread
  * per device, no collective).  rho0s/rhoTs: n_pairs*P doubles,

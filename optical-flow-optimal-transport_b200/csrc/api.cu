@@ -27,11 +27,13 @@ void set_error(const char *fmt, ...)
 using namespace foto;
 
 // ------------------------------------------------------------------------------- context
-struct DevResult {          // written by kernels, copied to the pinned mirror once per outer step
+struct DevResult {          // written by kernels, mirrored in pinned host memory
     double crit[2];         // numerator / denominator sums of the stopping criterion
     int cg_iters, cg_info;  // scipy-style (iterations, info)
     int error, pad;
+    OuterState outer;       // ALG2 outer loop as decided on the device (k_outer_decide)
 };
+static const int kLookSlots = 4;                          // pinned mirrors / events of the last outer iterations
 
 enum Cat { CAT_RHS = 0, CAT_CG, CAT_PROX, CAT_FLOW, CAT_GN, CAT_COUNT };
 
@@ -46,7 +48,10 @@ struct foto_ctx {
     double *sync_partials = nullptr;
     double *prox_partials = nullptr;
     DevResult *d_res = nullptr;
-    DevResult *h_res = nullptr;                       // pinned
+    DevResult *h_res = nullptr;                       // pinned, kLookSlots entries ([0]: fetch_result)
+    cudaEvent_t look_ev[kLookSlots] = {};
+    char *d_trace = nullptr, *h_trace = nullptr;      // per outer iteration: crit (double), cg_iters, cg_info (int)
+    int trace_cap = 0;
     int cg_grid = 0, cg_block = 0, gn_grid = 0, gn_block = 0;
     int cg_variant = -1;
     bool profiling = false;
@@ -58,6 +63,9 @@ struct foto_ctx {
     cudaEvent_t watch[2] = {nullptr, nullptr};
     OnchipScratch onchip;
     DctTables dct;
+    double *metric_partials = nullptr;                // foto_flow_metrics_dev / foto_warp_dev
+    char *warp_tmp = nullptr; size_t warp_tmp_bytes = 0;
+    char *pin = nullptr; size_t pin_bytes = 0;        // pinned staging of foto_solve_batch_u8
 };
 
 static const int kProxMaxBlocks = 148 * 8;
@@ -158,7 +166,8 @@ extern "C" int foto_ctx_create(int device, foto_ctx **out)
         CUDA_TRY(cudaMalloc((void **)&c->d_res, sizeof(DevResult)));
         CUDA_TRY(cudaMemset(c->d_res, 0, sizeof(DevResult)));
         CUDA_TRY(cudaMemset(c->sync_counter, 0, 256));
-        CUDA_TRY(cudaMallocHost((void **)&c->h_res, sizeof(DevResult)));
+        CUDA_TRY(cudaMallocHost((void **)&c->h_res, kLookSlots * sizeof(DevResult)));
+        for (int i = 0; i < kLookSlots; i++) CUDA_TRY(cudaEventCreateWithFlags(&c->look_ev[i], cudaEventDisableTiming));
         FOTO_TRY(cg_stream_config(device, &c->cg_grid, &c->cg_block));
         FOTO_TRY(gn_pcg_config(device, &c->gn_grid, &c->gn_block));
         return FOTO_OK;
@@ -176,8 +185,12 @@ extern "C" void foto_ctx_destroy(foto_ctx *c)
     c->stream = c->own_stream;
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (auto e : c->watch) if (e) cudaEventDestroy(e);
+    for (auto e : c->look_ev) if (e) cudaEventDestroy(e);
+    cudaFree(c->d_trace);
+    if (c->h_trace) cudaFreeHost(c->h_trace);
     cudaFree(c->ws); cudaFree(c->io); cudaFree(c->sync_counter); cudaFree(c->sync_partials);
-    cudaFree(c->prox_partials); cudaFree(c->d_res);
+    cudaFree(c->prox_partials); cudaFree(c->d_res); cudaFree(c->metric_partials); cudaFree(c->warp_tmp);
+    if (c->pin) cudaFreeHost(c->pin);
     onchip_release(c->onchip);
     cudaFree(c->dct.base);
     if (c->h_res) cudaFreeHost(c->h_res);
@@ -311,6 +324,7 @@ static int run_cg(foto_ctx *c, const Dims &d, const double *F, double *phi, doub
     else { set_error("unknown Poisson back-end %d", backend); return FOTO_ERR_ARG; }
     a.sync.counter = c->sync_counter; a.sync.partials = c->sync_partials; a.sync.error = &c->d_res->error;
     a.out = &c->d_res->cg_iters;
+    a.skip = d.skip;
     // kernel choice: 0 streaming (textbook recurrences), 2 on-chip single-reduction, -1 auto = on-chip when the grid
     // fits (only for the truncated cg_parity solve the single-reduction form was validated on)
     const bool fits_fused = cg_fused_fits(c->onchip, c->device, d.Nt, d.Ny, d.Nx);
@@ -346,34 +360,63 @@ extern "C" int foto_solve_dev(foto_ctx *c, const double *d_rho0, const double *d
     double *mu = cv.take(3ull * d.N), *q = cv.take(3ull * d.N), *F = cv.take(d.N), *phi = cv.take(d.N);
     double *work = cv.take(4ull * d.N);          // CG vectors r, p0, p1, q (contiguous, stride N)
 
+    // trace of the outer loop on the device + pinned mirror
+    if (c->trace_cap < max_it) {
+        if (c->d_trace) { CUDA_TRY(cudaFree(c->d_trace)); c->d_trace = nullptr; }
+        if (c->h_trace) { CUDA_TRY(cudaFreeHost(c->h_trace)); c->h_trace = nullptr; }
+        c->trace_cap = 0;
+        const int cap = max_it < 128 ? 128 : max_it;
+        CUDA_TRY(cudaMalloc((void **)&c->d_trace, (size_t)cap * 16));
+        CUDA_TRY(cudaMallocHost((void **)&c->h_trace, (size_t)cap * 16));
+        c->trace_cap = cap;
+    }
+    OuterTrace tr;
+    tr.crit = (double *)c->d_trace; tr.cg_iters = (int *)(c->d_trace + (size_t)c->trace_cap * 8); tr.cg_info = tr.cg_iters + c->trace_cap;
+    CUDA_TRY(cudaMemsetAsync(&c->d_res->outer, 0, sizeof(OuterState), c->stream));
+
     launch_init_state(c->stream, d, d_rho0, d_rhoT, mu, q);
     c->stats.launches++;
-    double crit = -1.0;
-    int outer = 0;
-    for (int it = 0; it < max_it; it++) {
+    // The ALG2 loop (benamou_brenier.py:204-258).  The stopping rule is evaluated on the device (k_outer_decide), and
+    // the host stays `look` iterations ahead: iteration it+1 is enqueued before the result of iteration it is known
+    // and its kernels return at once if iteration it stopped the loop (Dims::skip), so the device never waits for a
+    // host round trip between outer iterations.  dct_exact (several library kernels per solve) keeps look = 0.
+    const int look = backend == FOTO_POISSON_DCT_EXACT ? 0 : 1;
+    d.skip = look ? &c->d_res->outer.done : nullptr;
+    int outer = 0, enq = 0;
+    bool done = false;
+    auto check = [&](int it) -> int {                     // result of outer iteration `it` (waits for it)
+        DevResult *h = c->h_res + (it % kLookSlots);
+        CUDA_TRY(cudaEventSynchronize(c->look_ev[it % kLookSlots]));
+        if (h->error) {
+            cudaMemsetAsync(&c->d_res->error, 0, sizeof(int), c->stream);
+            set_error("grid-barrier watchdog fired inside a persistent kernel");
+            return FOTO_ERR_TIMEOUT;
+        }
+        if (h->outer.done) { done = true; outer = h->outer.n_outer; }
+        return FOTO_OK;
+    };
+    for (int it = 0; it < max_it && !done; it++) {
+        if (it - look - 1 >= 0) FOTO_TRY(check(it - look - 1));
+        if (done) break;
         prof_begin(c, CAT_RHS);
         launch_rhs(c->stream, d, mu, q, d_rho0, d_rhoT, r, F);                 // stepA, right-hand side
         prof_end(c);
         FOTO_TRY(run_cg(c, d, F, phi, work, r, eps, backend));                 // stepA, Poisson solve
         prof_begin(c, CAT_PROX);
-        int blocks = launch_prox_dual(c->stream, d, phi, mu, q, r, c->prox_partials, kProxMaxBlocks);   // stepB + stepC
-        launch_crit_final(c->stream, c->prox_partials, blocks, c->d_res->crit);
+        int blocks = launch_prox_dual(c->stream, d, phi, mu, q, r, c->prox_partials, kProxMaxBlocks, c->num_sms);   // stepB + stepC
+        if (blocks < 0) return FOTO_ERR_CUDA;
+        launch_outer_decide(c->stream, c->prox_partials, blocks, c->d_res->crit, &c->d_res->cg_iters, &c->d_res->outer, tr,
+                            it, tol, max_it);
         prof_end(c);
         c->stats.launches += 3;
-        c->stats.rhs_cells += d.N; c->stats.prox_cells += d.N;
         CUDA_TRY(cudaGetLastError());
-        FOTO_TRY(fetch_result(c));
-        c->stats.cg_iterations += c->h_res->cg_iters;
-        c->stats.cg_cells += (long long)c->h_res->cg_iters * d.N;
-        if (cg_iters) cg_iters[it] = c->h_res->cg_iters;
-        if (cg_info) cg_info[it] = c->h_res->cg_info;
-        const double prev = crit;
-        crit = std::sqrt(c->h_res->crit[0] / (c->h_res->crit[1] + 1e-10));     // benamou_brenier.py:251
-        if (crit_trace) crit_trace[it] = crit;
-        outer = it + 1;
-        if (crit <= tol) break;                                                // benamou_brenier.py:254
-        if (prev >= 0 && std::fabs(prev - crit) < 1e-5) break;                 // benamou_brenier.py:256-258
+        CUDA_TRY(cudaMemcpyAsync(c->h_res + (it % kLookSlots), c->d_res, sizeof(DevResult), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaEventRecord(c->look_ev[it % kLookSlots], c->stream));
+        enq = it + 1;
     }
+    for (int it = enq - look - 1 < 0 ? 0 : enq - look - 1; it < enq && !done; it++) FOTO_TRY(check(it));
+    if (!done) { set_error("outer loop ended without a decision"); return FOTO_ERR_CUDA; }
+    CUDA_TRY(cudaMemcpyAsync(c->h_trace, c->d_trace, (size_t)c->trace_cap * 16, cudaMemcpyDeviceToHost, c->stream));
     if (n_outer) *n_outer = outer;
     prof_begin(c, CAT_FLOW);
     launch_flow(c->stream, d, phi, d_u, d_v, d_m);
@@ -382,6 +425,18 @@ extern "C" int foto_solve_dev(foto_ctx *c, const double *d_rho0, const double *d
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     prof_resolve(c);
+    {
+        const double *hc = (const double *)c->h_trace;
+        const int *hi = (const int *)(c->h_trace + (size_t)c->trace_cap * 8), *hf = hi + c->trace_cap;
+        for (int it = 0; it < outer; it++) {
+            c->stats.cg_iterations += hi[it];
+            c->stats.cg_cells += (long long)hi[it] * d.N;
+            if (crit_trace) crit_trace[it] = hc[it];
+            if (cg_iters) cg_iters[it] = hi[it];
+            if (cg_info) cg_info[it] = hf[it];
+        }
+        c->stats.rhs_cells += (long long)outer * d.N; c->stats.prox_cells += (long long)outer * d.N;
+    }
     return FOTO_OK;
 }
 
@@ -823,6 +878,60 @@ extern "C" int foto_flow_metrics(const double *u, const double *v, const double 
     return FOTO_OK;
 }
 
+// ------------------------------------------------------------------------------- device-resident ingest / egress
+extern "C" int foto_ingest_u8_dev(foto_ctx *c, const unsigned char *d_u8, int n, double *d_out)
+{
+    if (!c || !d_u8 || !d_out || n < 1) { set_error("foto_ingest_u8_dev: bad argument"); return FOTO_ERR_ARG; }
+    FOTO_TRY(ctx_bind(c));
+    launch_ingest_u8(c->stream, (unsigned int)n, d_u8, d_out);
+    c->stats.launches++;
+    CUDA_TRY(cudaGetLastError());
+    return FOTO_OK;
+}
+
+extern "C" int foto_pack_flo_dev(foto_ctx *c, const double *d_u, const double *d_v, int n, float *d_out)
+{
+    if (!c || !d_u || !d_v || !d_out || n < 1) { set_error("foto_pack_flo_dev: bad argument"); return FOTO_ERR_ARG; }
+    FOTO_TRY(ctx_bind(c));
+    launch_pack_flo(c->stream, (unsigned int)n, d_u, d_v, d_out);
+    c->stats.launches++;
+    CUDA_TRY(cudaGetLastError());
+    return FOTO_OK;
+}
+
+static const int kMetricPartials = 6 * 148 * 8 + 8;
+
+extern "C" int foto_flow_metrics_dev(foto_ctx *c, const double *d_u, const double *d_v, const double *d_ug, const double *d_vg,
+                                     int n, double *d_out6)
+{
+    if (!c || !d_u || !d_v || !d_ug || !d_vg || !d_out6 || n < 1) { set_error("foto_flow_metrics_dev: bad argument"); return FOTO_ERR_ARG; }
+    FOTO_TRY(ctx_bind(c));
+    if (!c->metric_partials) CUDA_TRY(cudaMalloc((void **)&c->metric_partials, kMetricPartials * sizeof(double)));
+    launch_flow_metrics(c->stream, (unsigned int)n, d_u, d_v, d_ug, d_vg, c->metric_partials, c->metric_partials + 6 * 148 * 8);
+    CUDA_TRY(cudaMemcpyAsync(d_out6, c->metric_partials + 6 * 148 * 8, 6 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    c->stats.launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return FOTO_OK;
+}
+
+extern "C" int foto_warp_dev(foto_ctx *c, const double *d_f1, const double *d_u, const double *d_v, int w, int h,
+                             const double *d_m, double *d_out, const double *d_igt, double *d_ie)
+{
+    if (!c || !d_f1 || !d_u || !d_v || !d_out || w < 1 || h < 1) { set_error("foto_warp_dev: bad argument"); return FOTO_ERR_ARG; }
+    FOTO_TRY(ctx_bind(c));
+    const size_t P = (size_t)w * h;
+    FOTO_TRY(ensure(&c->warp_tmp, &c->warp_tmp_bytes, Carver::bytes(P)));
+    launch_warp(c->stream, w, h, d_f1, d_u, d_v, d_m, (double *)c->warp_tmp, d_out);
+    c->stats.launches += 2;
+    if (d_igt && d_ie) {
+        if (!c->metric_partials) CUDA_TRY(cudaMalloc((void **)&c->metric_partials, kMetricPartials * sizeof(double)));
+        launch_ie_sumsq(c->stream, (unsigned int)P, d_out, d_igt, c->metric_partials, d_ie);
+        c->stats.launches += 2;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return FOTO_OK;
+}
+
 // ------------------------------------------------------------------------------- time-slab building blocks
 // One huge volume split into contiguous time slabs, one per rank (second row).  The
 // exchange steps (1-plane halos, the t <-> y all-to-all of the DCT, the 2-scalar all-reduce of the criterion)
@@ -868,7 +977,8 @@ extern "C" int foto_slab_prox_dev(foto_ctx *c, const double *phi, double *mu, do
     Dims d;
     FOTO_TRY(slab_dims(gNt, n0, nloc, Nx, Ny, cs, &d));
     FOTO_TRY(ctx_bind(c));
-    const int blocks = launch_prox_dual(c->stream, d, phi, mu, q, r, c->prox_partials, kProxMaxBlocks);
+    const int blocks = launch_prox_dual(c->stream, d, phi, mu, q, r, c->prox_partials, kProxMaxBlocks, c->num_sms);
+    if (blocks < 0) return FOTO_ERR_CUDA;
     launch_crit_final(c->stream, c->prox_partials, blocks, d_out2);
     c->stats.launches += 2;
     CUDA_TRY(cudaGetLastError());
@@ -977,5 +1087,52 @@ extern "C" int foto_gn_solve_batch(int n_pairs, const double *f1s, const double 
                            ms + i * P, &it, &info);
         if (iters) iters[i] = it;
         return rc;
+    });
+}
+
+// Batched ingest / egress: 8-bit frames in, .flo payload out, pinned staging per context.
+extern "C" int foto_solve_batch_u8(int n_pairs, const unsigned char *f0s, const unsigned char *f1s, int Nt, int Nx, int Ny,
+                                   double r, double tol, double eps, int max_it, int backend, const int *device_ids,
+                                   int n_dev, float *flo, double *ms, int *n_outer)
+{
+    if (!f0s || !f1s || !flo) { set_error("foto_solve_batch_u8: NULL argument"); return FOTO_ERR_ARG; }
+    Dims d;
+    FOTO_TRY(make_dims(Nt, Nx, Ny, &d));
+    const size_t P = d.P;
+    return run_batch(n_pairs, device_ids, n_dev, [&](foto_ctx *c, int i) -> int {
+        FOTO_TRY(ctx_bind(c));
+        // device: [u8 f0 | u8 f1] [rho0] [rhoT] [u] [v] [m] [flo payload]; pinned: [u8 f0 | u8 f1] [flo payload] [m]
+        const size_t u8b = (2 * P + 255) & ~size_t(255);
+        FOTO_TRY(ensure(&c->io, &c->io_bytes, u8b + 6 * Carver::bytes(P)));
+        const size_t pin_need = u8b + Carver::bytes(P) + Carver::bytes(P);
+        if (c->pin_bytes < pin_need) {
+            if (c->pin) { CUDA_TRY(cudaFreeHost(c->pin)); c->pin = nullptr; c->pin_bytes = 0; }
+            CUDA_TRY(cudaMallocHost((void **)&c->pin, pin_need));
+            c->pin_bytes = pin_need;
+        }
+        unsigned char *d8 = (unsigned char *)c->io;
+        double *base = (double *)(c->io + u8b);
+        const size_t st = Carver::bytes(P) / sizeof(double);
+        double *d0 = base, *dT = base + st, *du = base + 2 * st, *dv = base + 3 * st, *dm = base + 4 * st;
+        float *dflo = (float *)(base + 5 * st);
+        unsigned char *p8 = (unsigned char *)c->pin;
+        float *pflo = (float *)(c->pin + u8b);
+        double *pm = (double *)(c->pin + u8b + Carver::bytes(P));
+        memcpy(p8, f0s + (size_t)i * P, P); memcpy(p8 + P, f1s + (size_t)i * P, P);
+        CUDA_TRY(cudaMemcpyAsync(d8, p8, 2 * P, cudaMemcpyHostToDevice, c->stream));
+        launch_ingest_u8(c->stream, (unsigned int)P, d8, d0);
+        launch_ingest_u8(c->stream, (unsigned int)P, d8 + P, dT);
+        c->stats.launches += 2;
+        int outer = 0;
+        FOTO_TRY(foto_solve_dev(c, d0, dT, Nt, Nx, Ny, r, tol, eps, max_it, backend, du, dv, dm, nullptr, &outer, nullptr, nullptr));
+        launch_pack_flo(c->stream, (unsigned int)P, du, dv, dflo);
+        c->stats.launches++;
+        CUDA_TRY(cudaMemcpyAsync(pflo, dflo, 2 * P * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (ms) CUDA_TRY(cudaMemcpyAsync(pm, dm, P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        memcpy(flo + (size_t)i * 2 * P, pflo, 2 * P * sizeof(float));
+        if (ms) memcpy(ms + (size_t)i * P, pm, P * sizeof(double));
+        if (n_outer) n_outer[i] = outer;
+        return FOTO_OK;
     });
 }

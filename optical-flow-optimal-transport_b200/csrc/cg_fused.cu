@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
 {
     constexpr int CPT = NT * YPT;
     extern __shared__ double smem[];
+    if (a.skip && *a.skip) return;
     const int tid = threadIdx.x, cta = blockIdx.x, ncta = gridDim.x;
     const int Ny = a.Ny, Nx = a.Nx;
     const int by = cta / g.gx, bx = cta - by * g.gx;

@@ -34,6 +34,7 @@ struct Coef {            // matrix entries of A, exactly as the reference assemb
 __global__ void __launch_bounds__(512, 2) cg_stream_kernel(CgArgs a)
 {
     __shared__ double red[128];
+    if (a.skip && *a.skip) return;
     const unsigned int P = (unsigned int)a.Nx * (unsigned int)a.Ny;
     const unsigned int N = P * (unsigned int)a.Nt;
     const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x;

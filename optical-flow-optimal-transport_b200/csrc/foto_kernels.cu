@@ -6,6 +6,7 @@
 // separately (numpy / scipy sparse mat-vec), and keeping that rounding makes K1 and K4
 // bit-identical to it and keeps the truncated-CG iterates within 1e-11 of the reference.
 #include "foto_kernels.cuh"
+#include "prox_math.cuh"
 
 namespace foto {
 
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(kThreads, 8) k_rhs(Dims d, const double *__res
                                                    const double *__restrict__ rho0, const double *__restrict__ rhoT,
                                                    double r, double *__restrict__ F)
 {
+    if (d.skip && *d.skip) return;
     const unsigned int stride = gridDim.x * blockDim.x;
     const double *mu1 = mu + d.cs, *q1 = q + d.cs, *mu2 = mu + 2u * d.cs, *q2 = q + 2u * d.cs;
     auto has = [&](int nl) { const int gn = d.n0 + nl; return gn >= 0 && gn < d.gNt; };   // plane exists globally
@@ -85,49 +87,12 @@ __global__ void __launch_bounds__(kThreads, 8) k_rhs(Dims d, const double *__res
             if (gn == d.gNt - 1) s += (rhoT[i] - mu[k] + r * q[k]);
             F[k] = s;
             w_m = w_c; w_c = w_p;
-            if (has(n + 2)) w_p = wv(mu, q, r, k + 2u * d.P);
+            if (n + 2 <= d.Nt && has(n + 2)) w_p = wv(mu, q, r, k + 2u * d.P);   // local planes -1 .. Nt only
         }
     }
 }
 
-// --------------------------------------------------------------------------- stepB
-// Projection of (alpha, beta1, beta2) onto K = {alpha + |beta|^2/2 <= 0}
-// (benamou_brenier.py:123-147), with the algebraic forms SURVEY.md section 7 verified:
-//   4/3 a^3 + 4 a^2 + 4 a + 4/3 = 4/3 (a+1)^3,  cos(atan2(b2,b1)) = b1/rho, sin = b2/rho,
-//   pow(s, 1/3) = cbrt(s),  zh = c - (a+1)/(3c).
-__device__ __forceinline__ void project_K(double a, double b1, double b2, double &qa, double &qb1, double &qb2)
-{
-    const double rho2 = b1 * b1 + b2 * b2;
-    if (2.0 * a + rho2 <= 0.0) { qa = a; qb1 = b1; qb2 = b2; return; }
-    // One rsqrt gives rho and the direction (cos, sin) = (b1, b2)/rho; atan2(0, 0) = 0 -> (1, 0).
-    // K3 is fp64-instruction bound, not HBM bound, when written with sqrt + two divisions here and
-    // cbrt + a division below (52 % of the HBM roofline at 1080x1920x16); rsqrt/rcbrt halve the count.
-    double rho = 0.0, ct = 1.0, st = 0.0;
-    if (rho2 > 0.0) {
-        const double rinv = rsqrt(rho2);
-        rho = rho2 * rinv; ct = b1 * rinv; st = b2 * rinv;
-    }
-    const double a1 = a + 1.0;
-    const double cube = a1 * a1 * a1;
-    double aH, rhoH;
-    if (-32.0 * cube - 108.0 * rho2 < 0.0) {                 // single real root
-        const double rad = (4.0 / 3.0) * cube + 4.5 * rho2;
-        const double s = 0.35355339059327379 * rho + (1.0 / 6.0) * sqrt(rad);   // sqrt(2)/4
-        const double rc = rcbrt(s);                           // 1 / c,  c = s^(1/3) = s * rc^2
-        const double c = s * rc * rc;
-        const double zh = c - a1 * (rc * (1.0 / 3.0));        // c - (a+1)/(3c)
-        aH = -(zh * zh);
-        rhoH = 1.4142135623730951 * zh;
-    } else {                                                  // three real roots
-        const double t = -a1;
-        const double arg = 1.8371173070873836 * rho / (t * sqrt(t));            // (3/2)^(3/2)
-        const double zh = 1.6329931618554521 * sqrt(t) * cos(acos(arg) / 3.0);  // 2 sqrt(2/3)
-        aH = -0.5 * (zh * zh);
-        rhoH = zh;
-    }
-    qa = aH; qb1 = rhoH * ct; qb2 = rhoH * st;
-}
-
+// --------------------------------------------------------------------------- stepB (project_K: prox_math.cuh)
 __global__ void __launch_bounds__(kThreads) k_stepB(unsigned int N, const double *__restrict__ p, double *__restrict__ q)
 {
     const unsigned int stride = gridDim.x * blockDim.x;
@@ -149,6 +114,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_prox_dual(Dims d, const double 
                                                          double *__restrict__ partials)
 {
     __shared__ double red[64];
+    if (d.skip && *d.skip) return;
     double acc[2] = {0.0, 0.0};
     const unsigned int stride = gridDim.x * blockDim.x;
     // work item = (chunk of kTChunk time planes, column): marching keeps phi(n-1), phi(n), phi(n+1) in
@@ -172,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_prox_dual(Dims d, const double 
             const double gy = dw(phi, k, (unsigned int)d.Nx, y, d.Ny);
             const double m0 = n0, m1 = n1, m2 = n2;
             p_m = p_c; p_c = p_p;
-            if (has(n + 2)) p_p = phi[k + 2u * d.P];
+            if (n + 2 <= d.Nt && has(n + 2)) p_p = phi[k + 2u * d.P];      // local planes -1 .. Nt only (Nt = halo of a slab)
             if (n + 1 < ne) { n0 = mu[k + d.P]; n1 = mu[d.cs + k + d.P]; n2 = mu[2u * d.cs + k + d.P]; }
             double qa, qb1, qb2;
             project_K(gt + inv_r * m0, gx + inv_r * m1, gy + inv_r * m2, qa, qb1, qb2);
@@ -199,6 +165,30 @@ __global__ void __launch_bounds__(kThreads) k_crit_final(const double *__restric
     for (int b = threadIdx.x; b < blocks; b += blockDim.x) { acc[0] += partials[2 * b]; acc[1] += partials[2 * b + 1]; }
     block_sum<2>(acc, red);
     if (threadIdx.x == 0) { out2[0] = acc[0]; out2[1] = acc[1]; }
+}
+
+// Outer-loop bookkeeping on the device: crit = sqrt(sum rho |res| / (sum rho |grad_x phi|^2 + 1e-10)) and the
+// stopping rule "crit <= tol or |crit_prev - crit| < 1e-5 (from the second iteration on)" (benamou_brenier.py:251-258),
+// so that the host can enqueue the next iteration without waiting for this one (sqrt and the division are IEEE
+// correctly rounded on both sides: same bits as the host evaluation).
+__global__ void __launch_bounds__(kThreads) k_outer_decide(const double *__restrict__ partials, int blocks, double *__restrict__ sums2,
+                                                            const int *__restrict__ cg_out, OuterState *state, OuterTrace tr,
+                                                            int it, double tol, int max_it)
+{
+    __shared__ double red[64];
+    if (state->done) return;                             // uniform: written below only after the block-wide sums
+    double acc[2] = {0.0, 0.0};
+    for (int b = threadIdx.x; b < blocks; b += blockDim.x) { acc[0] += partials[2 * b]; acc[1] += partials[2 * b + 1]; }
+    block_sum<2>(acc, red);
+    if (threadIdx.x == 0) {
+        sums2[0] = acc[0]; sums2[1] = acc[1];
+        const double crit = sqrt(acc[0] / (acc[1] + 1e-10));
+        tr.crit[it] = crit; tr.cg_iters[it] = cg_out[0]; tr.cg_info[it] = cg_out[1];
+        const bool stop = crit <= tol || (it > 0 && fabs(state->crit_prev - crit) < 1e-5) || it + 1 >= max_it;
+        state->crit_prev = crit;
+        state->n_outer = it + 1;
+        if (stop) state->done = 1;
+    }
 }
 
 // --------------------------------------------------------------------------- K4
@@ -336,8 +326,13 @@ void launch_rhs(cudaStream_t st, Dims d, const double *mu, const double *q, cons
 }
 
 int launch_prox_dual(cudaStream_t st, Dims d, const double *phi, double *mu, double *q, double r, double *partials,
-                     int max_blocks)
+                     int max_blocks, int num_sms)
 {
+    if (prox_tma_eligible(d, phi, mu, q)) {              // TMA-staged variant (prox_tma.cu): whole volumes, even Nx
+        int blocks = 0;
+        if (launch_prox_dual_tma(st, d, phi, mu, q, r, partials, max_blocks, num_sms, &blocks) == FOTO_OK) return blocks;
+        return -1;
+    }
     int blocks = blocks_for(d.P, max_blocks);
     k_prox_dual<<<blocks, kThreads, 0, st>>>(d, phi, mu, q, r, 1.0 / r, partials);
     return blocks;
@@ -346,6 +341,12 @@ int launch_prox_dual(cudaStream_t st, Dims d, const double *phi, double *mu, dou
 void launch_crit_final(cudaStream_t st, const double *partials, int blocks, double *out2)
 {
     k_crit_final<<<1, kThreads, 0, st>>>(partials, blocks, out2);
+}
+
+void launch_outer_decide(cudaStream_t st, const double *partials, int blocks, double *crit_sums2, const int *cg_out,
+                         OuterState *state, OuterTrace trace, int it, double tol, int max_it)
+{
+    k_outer_decide<<<1, kThreads, 0, st>>>(partials, blocks, crit_sums2, cg_out, state, trace, it, tol, max_it);
 }
 
 void launch_stepB(cudaStream_t st, unsigned int N, const double *p, double *q)
@@ -430,7 +431,49 @@ __global__ void __launch_bounds__(256) k_sum6(const double *__restrict__ partial
     if (threadIdx.x == 0) { out6[0] = a[0]; out6[1] = a[1]; out6[2] = b[0]; out6[3] = a[2]; out6[4] = a[3]; out6[5] = b[1]; }
 }
 
+// utils.openGrayscaleImage: f.flatten() / 255 (utils.py:42) -- an IEEE division of two exact integers, as numpy's
+__global__ void __launch_bounds__(256) k_ingest_u8(unsigned int n, const unsigned char *__restrict__ in, double *__restrict__ out)
+{
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) out[k] = (double)in[k] / 255.0;
+}
+
+// utils.IE (utils.py:354): sum (255 I - 255 IGT)^2
+__global__ void __launch_bounds__(256) k_ie_partial(unsigned int n, const double *__restrict__ a, const double *__restrict__ b,
+                                                     double *__restrict__ partials)
+{
+    __shared__ double red[32];
+    double acc[1] = {0.0};
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const double d = 255.0 * a[k] - 255.0 * b[k];
+        acc[0] += d * d;
+    }
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc[0];
+}
+__global__ void __launch_bounds__(256) k_sum1(const double *__restrict__ partials, int blocks, double *__restrict__ out1)
+{
+    __shared__ double red[32];
+    double acc[1] = {0.0};
+    for (int i = threadIdx.x; i < blocks; i += blockDim.x) acc[0] += partials[i];
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) out1[0] = acc[0];
+}
+
 }  // namespace
+
+void launch_ingest_u8(cudaStream_t st, unsigned int n, const unsigned char *in, double *out)
+{
+    k_ingest_u8<<<blocks_for(n), 256, 0, st>>>(n, in, out);
+}
+
+void launch_ie_sumsq(cudaStream_t st, unsigned int n, const double *a, const double *b, double *partials, double *out1)
+{
+    const int blocks = blocks_for(n, 148 * 8);
+    k_ie_partial<<<blocks, 256, 0, st>>>(n, a, b, partials);
+    k_sum1<<<1, 256, 0, st>>>(partials, blocks, out1);
+}
 
 void launch_pack_flo(cudaStream_t st, unsigned int n, const double *u, const double *v, float *out)
 {

@@ -13,7 +13,18 @@ struct Dims {
     // globally.  Whole-volume calls use n0 = 0, gNt = Nt, cs = N.
     int n0, gNt;
     unsigned int cs;
+    // outer-loop pipelining (foto_solve_dev): kernels of a speculatively enqueued ALG2 iteration return at once when
+    // *skip != 0 (the iteration before met the stopping rule).  NULL: always run.
+    const int *skip = nullptr;
 };
+
+// device-side record of the ALG2 outer loop (benamou_brenier.py:204-258), written by k_outer_decide
+struct OuterState {
+    double crit_prev;       // criterion of the previous outer iteration
+    int done;               // stopping rule met (or max_it reached)
+    int n_outer;            // outer iterations completed
+};
+struct OuterTrace { double *crit; int *cg_iters; int *cg_info; };   // device arrays, one entry per outer iteration
 
 // ---- FOTO pointwise / stencil kernels (foto_kernels.cu) --------------------------------
 // mu <- [linear-in-time density | 0 | 0],  q <- 0          (benamou_brenier.py:191-194)
@@ -23,9 +34,18 @@ void launch_rhs(cudaStream_t st, Dims d, const double *mu, const double *q, cons
                 const double *rhoT, double r, double *F);
 // K3: grad_st phi, stepB, stepC, clamp, criterion partial sums (benamou_brenier.py:213-251)
 // partials: 2*blocks doubles; returns the number of blocks used.
+// Returns the number of blocks used (= partial-sum pairs written), or -1 on a launch error (foto_last_error).
 int launch_prox_dual(cudaStream_t st, Dims d, const double *phi, double *mu, double *q, double r,
-                     double *partials, int max_blocks);
+                     double *partials, int max_blocks, int num_sms);
+// TMA-staged K3 (prox_tma.cu)
+bool prox_tma_eligible(const Dims &d, const double *phi, const double *mu, const double *q);
+int launch_prox_dual_tma(cudaStream_t st, Dims d, const double *phi, double *mu, double *q, double r, double *partials,
+                         int max_blocks, int num_sms, int *blocks_out);
 void launch_crit_final(cudaStream_t st, const double *partials, int blocks, double *out2);
+// criterion of outer iteration `it` from the K3 partial sums + the reference's stopping rule
+// (benamou_brenier.py:246-258), decided on the device; cg_out = the (iterations, info) pair the Poisson kernel wrote
+void launch_outer_decide(cudaStream_t st, const double *partials, int blocks, double *crit_sums2, const int *cg_out,
+                         OuterState *state, OuterTrace trace, int it, double tol, int max_it);
 // stepB alone (benamou_brenier.py:93-149)
 void launch_stepB(cudaStream_t st, unsigned int N, const double *p, double *q);
 // K4: trajectories + luminosity (utils.py:44-99,148-183)
@@ -37,6 +57,9 @@ void launch_warp(cudaStream_t st, int w, int h, const double *f1, const double *
 void launch_pack_flo(cudaStream_t st, unsigned int n, const double *u, const double *v, float *out);
 void launch_flow_metrics(cudaStream_t st, unsigned int n, const double *u, const double *v, const double *ug,
                          const double *vg, double *partials, double *out6);
+void launch_ingest_u8(cudaStream_t st, unsigned int n, const unsigned char *in, double *out);
+// sum (255 a - 255 b)^2 (utils.IE, utils.py:354); partials: >= 1184 doubles
+void launch_ie_sumsq(cudaStream_t st, unsigned int n, const double *a, const double *b, double *partials, double *out1);
 // generic tridiagonal-along-one-axis apply used by foto_op_apply
 void launch_axis_apply(cudaStream_t st, const double *in, double *out, const double *lo, const double *di,
                        const double *up, int transpose, unsigned int stride, int len, unsigned int total,
@@ -54,6 +77,7 @@ struct CgArgs {
     int maxiter;
     SyncState sync;
     int *out;               // [0] iterations, [1] info (0 converged / maxiter)
+    const int *skip = nullptr;   // see Dims::skip
 };
 // Returns FOTO_OK or an error code.  grid/block are chosen by cg_stream_config().
 int cg_stream_config(int device, int *grid, int *block);

@@ -27,7 +27,8 @@ EXPORTS = [
     "foto_tri_coeffs", "foto_gn_solve", "foto_gn_system", "foto_warp_apply",
     "foto_solve_batch", "foto_gn_solve_batch", "foto_pack_flo", "foto_flow_metrics",
     "foto_ctx_set_stream", "foto_slab_rhs_dev", "foto_slab_prox_dev", "foto_dct_xy_dev", "foto_dct_t_solve_dev",
-    "foto_flow_dev",
+    "foto_flow_dev", "foto_ingest_u8_dev", "foto_pack_flo_dev", "foto_flow_metrics_dev", "foto_warp_dev",
+    "foto_solve_batch_u8",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -97,8 +98,8 @@ def _check(rc):
 
 
 def set_default_cg_variant(variant):
-    """-1 auto (fastest kernel that fits: single-reduction on-chip, textbook on-chip, streaming), 0 streaming,
-    1 on-chip with the textbook CG recurrences, 2 on-chip single-reduction.  Applies to the Poisson and the GN solve."""
+    """-1 auto (the on-chip single-reduction kernel when the grid fits, else streaming), 0 streaming (textbook CG
+    recurrences), 2 on-chip single-reduction.  Applies to the Poisson and the GN solve."""
     _check(lib().foto_set_default_cg_variant(int(variant)))
 
 
@@ -111,6 +112,14 @@ def _a(x, n=None):
     x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
     if n is not None and x.size != n:
         raise ValueError(f"expected {n} values, got {x.size}")
+    return x
+
+
+def _out(x, n):
+    """A caller-provided output buffer: must be a C-contiguous float64 numpy array of exactly n values."""
+    if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags["C_CONTIGUOUS"] and x.size == n
+            and x.flags["WRITEABLE"]):
+        raise ValueError(f"output buffer must be a writable C-contiguous float64 numpy array of {n} values")
     return x
 
 
@@ -278,6 +287,36 @@ def solve_batch(rho0s, rhoTs, Nt, Nx, Ny, r=1.0, convergence_tol=0.3, reg_epsilo
     return us, vs, ms, outer
 
 
+def solve_batch_u8(f0s_u8, f1s_u8, Nt, Nx, Ny, r=1.0, convergence_tol=0.3, reg_epsilon=1e-3, max_it=100,
+                   backend=POISSON_CG_PARITY, devices=None, want_m=True):
+    """Batched ingest + solve + .flo egress: 8-bit grey frames in (n, P), float32 .flo payloads out (n, 2P)
+    [+ m (n, P)], sharded over `devices`.  `save_flo_payload` writes a payload as a .flo file."""
+    P = int(Nx) * int(Ny)
+    f0s = np.ascontiguousarray(f0s_u8, dtype=np.uint8).reshape(-1, P)
+    f1s = np.ascontiguousarray(f1s_u8, dtype=np.uint8).reshape(-1, P)
+    n = f0s.shape[0]
+    if f1s.shape[0] != n:
+        raise ValueError("both frame stacks must hold the same number of images")
+    flo = np.empty((n, 2 * P), dtype=np.float32)
+    ms = np.empty((n, P)) if want_m else None
+    outer = np.zeros(n, dtype=np.int32)
+    keep, dp, nd = _devices(devices)
+    u8p = C.POINTER(C.c_ubyte)
+    _check(lib().foto_solve_batch_u8(n, f0s.ctypes.data_as(u8p), f1s.ctypes.data_as(u8p), int(Nt), int(Nx), int(Ny), _d(r),
+                                     _d(convergence_tol), _d(reg_epsilon), int(max_it), int(backend), dp, nd,
+                                     flo.ctypes.data_as(C.POINTER(C.c_float)), _p(ms) if want_m else None,
+                                     outer.ctypes.data_as(_ip)))
+    return flo, ms, outer
+
+
+def save_flo_payload(w, h, payload, pathname):
+    """utils.saveFlo's file (utils.py:273-292) from a packed float32 payload: magic, w, h, interleaved (u, v)."""
+    with open(pathname, "wb") as f:
+        np.array([202021.25], dtype=np.float32).tofile(f)
+        np.array([w, h], dtype=np.int32).tofile(f)
+        np.ascontiguousarray(payload, dtype=np.float32).tofile(f)
+
+
 def gn_solve_batch(f1s, f2s, w, h, alpha, lam, rtol=0.0, max_it=0, devices=None):
     P = int(w) * int(h)
     f1s = np.ascontiguousarray(f1s, dtype=np.float64).reshape(-1, P)
@@ -359,6 +398,23 @@ class Context:
         vp = C.c_void_p
         _check(lib().foto_flow_dev(self._h, vp(d_phi), int(Nt), int(Nx), int(Ny), vp(d_u), vp(d_v), vp(d_m)))
 
+    # ---- device-resident ingest / egress (raw device pointers) --------------------------------
+    def ingest_u8(self, d_u8, n, d_out):
+        _check(lib().foto_ingest_u8_dev(self._h, C.c_void_p(d_u8), int(n), C.c_void_p(d_out)))
+
+    def pack_flo_dev(self, d_u, d_v, n, d_out_f32):
+        vp = C.c_void_p
+        _check(lib().foto_pack_flo_dev(self._h, vp(d_u), vp(d_v), int(n), vp(d_out_f32)))
+
+    def flow_metrics_dev(self, d_u, d_v, d_ug, d_vg, n, d_out6):
+        vp = C.c_void_p
+        _check(lib().foto_flow_metrics_dev(self._h, vp(d_u), vp(d_v), vp(d_ug), vp(d_vg), int(n), vp(d_out6)))
+
+    def warp_dev(self, d_f1, d_u, d_v, w, h, d_m, d_out, d_igt=None, d_ie=None):
+        vp = C.c_void_p
+        _check(lib().foto_warp_dev(self._h, vp(d_f1), vp(d_u), vp(d_v), int(w), int(h), vp(d_m) if d_m else None, vp(d_out),
+                                   vp(d_igt) if d_igt else None, vp(d_ie) if d_ie else None))
+
     def event_record(self, which):
         _check(lib().foto_ctx_event_record(self._h, int(which)))
 
@@ -371,6 +427,10 @@ class Context:
                    max_it=100, backend=POISSON_CG_PARITY):
         """Host-buffer solve into preallocated numpy outputs (H2D + solve + D2H on this context)."""
         n_outer = C.c_int(0)
+        P = int(Nx) * int(Ny)
+        rho0, rhoT = _a(rho0, P), _a(rhoT, P)
+        for o in (u, v, m):
+            _out(o, P)
         _check(lib().foto_solve_host(self._h, _p(rho0), _p(rhoT), int(Nt), int(Nx), int(Ny), _d(r),
                                      _d(convergence_tol), _d(reg_epsilon), int(max_it), int(backend),
                                      _p(u), _p(v), _p(m), None, C.byref(n_outer), None, None))
@@ -378,6 +438,10 @@ class Context:
 
     def gn_solve_host(self, f1, f2, w, h, alpha, lam, u, v, m, rtol=0.0, max_it=0):
         it = C.c_int(0); info = C.c_int(0)
+        P = int(w) * int(h)
+        f1, f2 = _a(f1, P), _a(f2, P)
+        for o in (u, v, m):
+            _out(o, P)
         _check(lib().foto_gn_solve_host(self._h, _p(f1), _p(f2), int(w), int(h), _d(alpha), _d(lam), _d(rtol),
                                         int(max_it), _p(u), _p(v), _p(m), C.byref(it), C.byref(info)))
         return it.value

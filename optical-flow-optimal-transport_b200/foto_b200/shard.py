@@ -15,6 +15,45 @@ def _dist():
     return dist if dist.is_available() and dist.is_initialized() else None
 
 
+class WorkQueue:
+    """Dynamic work sharing between the ranks of a torchrun job: an atomic counter in the process group's key-value
+    store (TCPStore.add), so that a rank that drew short solves (outer and CG iteration counts are data dependent)
+    takes the next item instead of idling -- the multi-process counterpart of the atomic work queue inside
+    foto_solve_batch.  No collective and no data on the path: only item indices travel.  Without a process group
+    it counts locally.  `name` must be unique per queue (counters are never reset)."""
+
+    def __init__(self, name, n_items, chunk=1):
+        self.n, self.chunk, self.key = int(n_items), max(int(chunk), 1), f"foto_b200/wq/{name}"
+        self._local, self._have = 0, []
+        d = _dist()
+        self._store = None
+        if d is not None:
+            from torch.distributed import distributed_c10d as c10d
+            self._store = c10d._get_default_store()
+
+    def next(self):
+        """Next unclaimed item index, or None when the queue is empty."""
+        if not self._have:
+            if self._store is None:
+                first = self._local; self._local += self.chunk
+            else:
+                first = self._store.add(self.key, self.chunk) - self.chunk
+            self._have = [i for i in range(first, first + self.chunk) if i < self.n][::-1]
+            if not self._have:
+                return None
+        return self._have.pop()
+
+
+def gather_objects(obj):
+    """List of every rank's picklable `obj` on every rank (single-process: [obj])."""
+    d = _dist()
+    if d is None:
+        return [obj]
+    out = [None] * d.get_world_size()
+    d.all_gather_object(out, obj)
+    return out
+
+
 def barrier():
     d = _dist()
     if d is not None:

@@ -320,15 +320,78 @@ def gold_full():
          u=g["u"][sub], v=g["v"][sub], m=g["m"][sub], seconds=g["seconds"], **stats)
 
 
+# ----------------------------------------------------------------------------- config-3 shapes, dataset tools, metrics
+def _full_case(tag, name, h, w, f0, f1, kw):
+    print(f"  {tag}: reference FOTO {h}x{w} ...", flush=True)
+    res = run_solve(f0, f1, 4, w, h, **kw)
+    sub = np.arange(0, h * w, 13)
+    stats = {k + "_stats": np.array([res[k].sum(), np.abs(res[k]).sum(), np.abs(res[k]).max(),
+                                     np.sqrt((res[k] ** 2).sum())]) for k in "uvm"}
+    print(f"  {tag} ({name}): {len(res['crit'])} outer, cg {res['cg_iters'].tolist()}, {float(res['seconds']):.1f}s")
+    save(tag, f0_u8=u8(f0), f1_u8=u8(f1), dims=np.array([h, w, 4]),
+         params=np.array([kw["r"], kw["convergence_tol"], kw["reg_epsilon"], kw["max_it"]]), sub=sub,
+         u=res["u"][sub], v=res["v"][sub], m=res["m"][sub], crit=res["crit"], cg_iters=res["cg_iters"],
+         seconds=res["seconds"], **stats)
+
+
+def gold_config3ref():
+    """One pair per config-3 shape that config 1 does not cover, from the unmodified reference: Grove2/0 (480x640, the
+    shape that runs the large on-chip CG variant with x in global memory) and Venus/0 (380x420)."""
+    kw = dict(synth.CONFIG3_PARAMS)
+    for seq, tag in (("Grove2", "foto_480x640_grove2"), ("Venus", "foto_380x420_venus")):
+        (name, h, w, f0, f1), = synth.config3_pairs(sequences=[seq], perturbations=[0])
+        _full_case(tag, name, h, w, f0, f1, kw)
+
+
+def gold_lum():
+    """Outputs of the reference's dataset tools themselves (bin/create_lum_dataset.py, bin/normalize_image.py, run as
+    scripts on PNG files) and of the metric functions (utils.py:294-354)."""
+    import subprocess
+    import tempfile
+    from PIL import Image
+    rng = np.random.default_rng(707)
+    out = {}
+    env = dict(os.environ, PYTHONPATH=REF)
+    with tempfile.TemporaryDirectory() as tmp:
+        for tag, (h, w) in {"a": (40, 56), "b": (97, 146), "c": (33, 21)}.items():
+            a = rng.integers(0, 256, (h, w), dtype=np.uint8); b = rng.integers(0, 200, (h, w), dtype=np.uint8)
+            pa, pb, po, po2 = (os.path.join(tmp, n) for n in ("a.png", "b.png", "o.png", "o2.png"))
+            Image.fromarray(a, "L").save(pa); Image.fromarray(b, "L").save(pb)
+            out[f"{tag}/a"] = a; out[f"{tag}/b"] = b
+            for seed in (1, 12346, 12352):
+                subprocess.check_call([sys.executable, os.path.join(REF, "bin", "create_lum_dataset.py"), pa, po, str(seed)], env=env)
+                out[f"{tag}/lum/{seed}"] = np.asarray(Image.open(po).convert("L"))
+            subprocess.check_call([sys.executable, os.path.join(REF, "bin", "normalize_image.py"), pa, pb, po, po2], env=env)
+            out[f"{tag}/norm1"] = np.asarray(Image.open(po).convert("L")); out[f"{tag}/norm2"] = np.asarray(Image.open(po2).convert("L"))
+    save("lum", **out)
+    # metrics: EE / AE with the > 50 px and NaN filters, IE
+    out = {}
+    for tag, (h, w, amp) in {"a": (19, 27, 1.5), "b": (31, 44, 30.0), "c": (8, 8, 0.0)}.items():
+        n = h * w
+        u = rng.standard_normal(n) * amp; v = rng.standard_normal(n) * amp
+        ug = u + rng.standard_normal(n) * 0.3; vg = v + rng.standard_normal(n) * 0.3
+        ug[::11] += 80.0                                  # endpoint errors beyond the 50 px filter
+        if tag == "c":
+            ug[:] = u; vg[:] = v                          # identical flows: arccos argument rounds above 1 -> NaN filter
+        I = rng.random(n); IGT = rng.random(n)
+        with np.errstate(invalid="ignore"):
+            ee = ref_utils.EE(w, h, u, v, ug, vg); ae = ref_utils.AE(w, h, u, v, ug, vg)
+        out.update({f"{tag}/dims": np.array([h, w]), f"{tag}/u": u, f"{tag}/v": v, f"{tag}/ug": ug, f"{tag}/vg": vg,
+                    f"{tag}/I": I, f"{tag}/IGT": IGT, f"{tag}/EE": np.array(ee), f"{tag}/AE": np.array(ae),
+                    f"{tag}/IE": np.float64(ref_utils.IE(w, h, I, IGT))})
+        print(f"  metrics {tag}: EE {ee}, AE {ae}")
+    save("metrics", **out)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also the 388x584 cases")
-    ap.add_argument("--only", default="", help="comma list: operators,stepB,stepA,foto,gn,flow,warp,full")
+    ap.add_argument("--only", default="", help="comma list: operators,stepB,stepA,foto,gn,flow,warp,lum,full,config3ref")
     a = ap.parse_args()
     print(f"numpy {np.__version__}, scipy {scipy.__version__}, reference at {REF}")
-    todo = a.only.split(",") if a.only else ["operators", "stepB", "stepA", "flow", "warp", "gn", "foto"]
-    if a.full and "full" not in todo:
-        todo.append("full")
+    todo = a.only.split(",") if a.only else ["operators", "stepB", "stepA", "flow", "warp", "lum", "gn", "foto"]
+    if a.full:
+        todo += [t for t in ("full", "config3ref") if t not in todo]
     for name in todo:
         print(f"[{name}]", flush=True)
         globals()["gold_" + name]()

@@ -48,7 +48,45 @@ def test_sharding_gather_and_max_with_gloo():
     np.testing.assert_array_equal(np.array(full0), expect)
 
 
+def _queue_worker(rank, world, port, n_items, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    wq = shard.WorkQueue("t1", n_items, chunk=2 if rank else 1)
+    shard.barrier()
+    got = []
+    while True:
+        i = wq.next()
+        if i is None:
+            break
+        got.append(i)
+    stats = shard.gather_objects({"rank": rank, "n": len(got)})
+    q.put((rank, got, stats))
+    shard.barrier()
+    dist.destroy_process_group()
+
+
+def test_work_queue_hands_every_item_out_once_with_gloo():
+    """The shared queue bench.py and multi-process drivers draw pairs from: every index exactly once over the ranks."""
+    world, n_items = 2, 37
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_queue_worker, args=(r, world, port, n_items, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    items = sorted(res[0][1] + res[1][1])
+    assert items == list(range(n_items))
+    assert res[0][2] == res[1][2] and sum(s["n"] for s in res[0][2]) == n_items
+
+
 def test_single_process_identity():
+    wq = shard.WorkQueue("solo", 3)
+    assert [wq.next(), wq.next(), wq.next(), wq.next()] == [0, 1, 2, None]
+    assert shard.gather_objects(5) == [5]
     assert shard.shard_indices(7, 0, 1) == list(range(7))
     assert shard.max_over_ranks([3.0]) == [3.0]
     out = shard.gather_rows(np.ones((2, 4)), [0, 1], 2, 4)

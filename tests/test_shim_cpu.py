@@ -114,3 +114,35 @@ def test_scalar_trajectory_helper_matches_reference_golden(shim):
     for (x, y) in [(0, 0), (3, 2), (Nx - 1, Ny - 1)]:
         du, dv = ut.reconstructTrajectory(x, y, un, vn, Nx, Ny, Nt)
         assert du == g["b/u"][y * Nx + x] and dv == g["b/v"][y * Nx + x]
+
+
+def test_dataset_tools_match_the_reference_tools_byte_for_byte():
+    """synth.perturb_brightness / normalize_pair against PNGs written by the reference's own
+    bin/create_lum_dataset.py and bin/normalize_image.py (tests/golden/lum.npz, make_golden.py --only lum)."""
+    from foto_b200 import synth
+    g = load_golden("lum")
+    n = 0
+    for tag in ("a", "b", "c"):
+        a, b = g[f"{tag}/a"], g[f"{tag}/b"]
+        h, w = a.shape
+        for key in [k for k in g.files if k.startswith(f"{tag}/lum/")]:
+            seed = int(key.split("/")[-1])
+            mine = synth.perturb_brightness(a.ravel() / 255, h, w, seed)
+            np.testing.assert_array_equal(mine, g[key].ravel() / 255)      # what utils.openGrayscaleImage returns for that PNG
+            n += 1
+        m1, m2 = synth.normalize_pair(a.ravel() / 255, b.ravel() / 255)
+        np.testing.assert_array_equal(m1, g[f"{tag}/norm1"].ravel() / 255)
+        np.testing.assert_array_equal(m2, g[f"{tag}/norm2"].ravel() / 255)
+    assert n == 9
+
+
+def test_metrics_match_reference_goldens(shim):
+    """EE / AE (with the > 50 px and NaN filters) and IE against the reference's utils.py:294-354."""
+    g = load_golden("metrics")
+    for tag in ("a", "b", "c"):
+        h, w = map(int, g[f"{tag}/dims"])
+        u, v, ug, vg = (g[f"{tag}/{k}"] for k in ("u", "v", "ug", "vg"))
+        with np.errstate(invalid="ignore"):
+            np.testing.assert_allclose(shim["utils"].EE(w, h, u, v, ug, vg), g[f"{tag}/EE"], rtol=1e-13, atol=1e-15)
+            np.testing.assert_allclose(shim["utils"].AE(w, h, u, v, ug, vg), g[f"{tag}/AE"], rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(shim["utils"].IE(w, h, g[f"{tag}/I"], g[f"{tag}/IGT"]), g[f"{tag}/IE"], rtol=1e-14)
