@@ -319,8 +319,10 @@ def run_b200(args):
             traffic = json.load(open(tpath))
         sm_mhz = clocks.get("sm_mhz") or 1965.0
         onchip = {
-            "kernel": kname, "share_of_step": stats["cg_ms"] / dev_ms_rank, "avg_launch_ms": stats["cg_ms"] / max(stats["cg_launches"], 1),
-            "cg_iterations_per_launch": stats["cg_iterations"] / max(stats["cg_launches"], 1),
+            # launches that did work = outer iterations (the look-ahead also enqueues one launch per solve that returns at once)
+            "kernel": kname, "share_of_step": stats["cg_ms"] / dev_ms_rank, "avg_launch_ms": stats["cg_ms"] / max(log["outer"], 1),
+            "cg_iterations_per_launch": stats["cg_iterations"] / max(log["outer"], 1),
+            "launches_total": int(stats["cg_launches"]), "launches_with_work": log["outer"],
             "us_per_cg_iteration": us_iter, "cycles_per_cg_iteration": us_iter * sm_mhz,
             "algorithmic_88B_rate_GBs": CG_BYTES_PER_CELL_ITER * stats["cg_cells"] / cg_s / 1e9 if cg_s > 0 else 0.0,
             "algorithmic_88B_rate_note": "algorithmic bytes of SURVEY.md 8(d) over kernel time; the state (x, r, p, s, w) never leaves "

@@ -63,6 +63,9 @@ struct foto_ctx {
     cudaEvent_t watch[2] = {nullptr, nullptr};
     OnchipScratch onchip;
     DctTables dct;
+    DctTables gn_dct64;                               // fp64 DCT tables of the GN image shape (source of gn_tb)
+    GnDctTables gn_tb;
+    char *gn_state = nullptr, *h_gn_state = nullptr;  // device state of the spectral GN solve + pinned mirrors (kLookSlots)
     double *metric_partials = nullptr;                // foto_flow_metrics_dev / foto_warp_dev
     char *warp_tmp = nullptr; size_t warp_tmp_bytes = 0;
     char *pin = nullptr; size_t pin_bytes = 0;        // pinned staging of foto_solve_batch_u8
@@ -190,6 +193,8 @@ extern "C" void foto_ctx_destroy(foto_ctx *c)
     if (c->h_trace) cudaFreeHost(c->h_trace);
     cudaFree(c->ws); cudaFree(c->io); cudaFree(c->sync_counter); cudaFree(c->sync_partials);
     cudaFree(c->prox_partials); cudaFree(c->d_res); cudaFree(c->metric_partials); cudaFree(c->warp_tmp);
+    cudaFree(c->gn_dct64.base); cudaFree(c->gn_tb.base); cudaFree(c->gn_state);
+    if (c->h_gn_state) cudaFreeHost(c->h_gn_state);
     if (c->pin) cudaFreeHost(c->pin);
     onchip_release(c->onchip);
     cudaFree(c->dct.base);
@@ -204,7 +209,7 @@ extern "C" int foto_ctx_reset_stats(foto_ctx *c) { if (!c) return FOTO_ERR_ARG; 
 extern "C" int foto_ctx_get_stats(foto_ctx *c, foto_stats *out) { if (!c || !out) return FOTO_ERR_ARG; *out = c->stats; return FOTO_OK; }
 extern "C" int foto_ctx_set_cg_variant(foto_ctx *c, int v)
 {
-    if (!c || v < -1 || v > 2 || v == 1) { set_error("cg variant must be -1 (auto), 0 (streaming) or 2 (on-chip single-reduction)"); return FOTO_ERR_ARG; }
+    if (!c || v < -1 || v > 3 || v == 1) { set_error("cg variant must be -1 (auto), 0 (streaming), 2 (on-chip single-reduction) or 3 (GN: spectral preconditioner)"); return FOTO_ERR_ARG; }
     c->cg_variant = v;
     return FOTO_OK;
 }
@@ -329,7 +334,8 @@ static int run_cg(foto_ctx *c, const Dims &d, const double *F, double *phi, doub
     // fits (only for the truncated cg_parity solve the single-reduction form was validated on)
     const bool fits_fused = cg_fused_fits(c->onchip, c->device, d.Nt, d.Ny, d.Nx);
     if (c->cg_variant == 2 && !fits_fused) { set_error("grid %dx%dx%d does not fit the single-reduction on-chip CG variant", d.Nt, d.Ny, d.Nx); return FOTO_ERR_ARG; }
-    const int kind = (c->cg_variant == 2 || (c->cg_variant == -1 && fits_fused && backend == FOTO_POISSON_CG_PARITY)) ? 3 : 0;
+    const bool want_auto = c->cg_variant == -1 || c->cg_variant == 3;       // 3 selects a GN solver only
+    const int kind = (c->cg_variant == 2 || (want_auto && fits_fused && backend == FOTO_POISSON_CG_PARITY)) ? 3 : 0;
     prof_begin(c, CAT_CG);
     if (kind == 3) FOTO_TRY(launch_cg_fused(c->stream, a, c->device, c->onchip));
     else FOTO_TRY(launch_cg_stream(c->stream, a, c->cg_grid, c->cg_block));
@@ -441,6 +447,87 @@ extern "C" int foto_solve_dev(foto_ctx *c, const double *d_rho0, const double *d
 }
 
 // ------------------------------------------------------------------------------- GN solve
+static int ensure_dct_tables_2d(foto_ctx *c, DctTables &t, int h, int w)
+{
+    if (t.base && t.Ny == h && t.Nx == w) return FOTO_OK;
+    if (t.base) { CUDA_TRY(cudaFree(t.base)); t = DctTables(); }
+    const int n[2] = {w, h};
+    std::vector<double> host;
+    std::vector<size_t> off;
+    for (int a = 0; a < 2; a++) {
+        std::vector<double> C, Ct, lam;
+        dct_host_tables(n[a], C, Ct, lam);
+        off.push_back(host.size()); host.insert(host.end(), C.begin(), C.end());
+        off.push_back(host.size()); host.insert(host.end(), Ct.begin(), Ct.end());
+        off.push_back(host.size()); host.insert(host.end(), lam.begin(), lam.end());
+    }
+    CUDA_TRY(cudaMalloc((void **)&t.base, host.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(t.base, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));          // host vector goes out of scope
+    t.Cx = t.base + off[0]; t.CxT = t.base + off[1]; t.lam_x = t.base + off[2];
+    t.Cy = t.base + off[3]; t.CyT = t.base + off[4]; t.lam_y = t.base + off[5];
+    t.Nt = 0; t.Ny = h; t.Nx = w;
+    return FOTO_OK;
+}
+
+// classical.py:113-130 with the spectral preconditioner (gn_dct.cu): iterations are enqueued in chunks, the host
+// reads the device's `done` flag one chunk behind
+static int gn_solve_spectral(foto_ctx *c, const double *d_f1, const double *d_f2, int w, int h, double alpha, double lambda,
+                             double rtol, int max_it, double *d_u, double *d_v, double *d_m, int *iters, int *info)
+{
+    const size_t P = (size_t)w * h;
+    FOTO_TRY(ensure_dct_tables_2d(c, c->gn_dct64, h, w));
+    FOTO_TRY(gn_dct_prepare_tables(c->stream, c->gn_dct64, w, h, c->gn_tb));
+    if (!c->gn_state) {
+        CUDA_TRY(cudaMalloc((void **)&c->gn_state, 256));
+        CUDA_TRY(cudaMallocHost((void **)&c->h_gn_state, kLookSlots * 256));
+    }
+    const size_t n32 = ((size_t)3 * c->gn_tb.hp * c->gn_tb.wp + 1) / 2;     // one padded fp32 volume, in doubles
+    FOTO_TRY(ensure(&c->ws, &c->ws_bytes, 2 * Carver::bytes(P) + 7 * Carver::bytes(3 * P) + Carver::bytes(8) + Carver::bytes(6 * 1184) +
+                                              Carver::bytes(3 * 592) + 4 * Carver::bytes(n32)));
+    Carver cv(c->ws);
+    double *fx = cv.take(P), *fy = cv.take(P), *dinv = cv.take(3 * P), *b = cv.take(3 * P);
+    GnDctArgs a;
+    a.fx = fx; a.fy = fy; a.f2 = d_f2; a.b = b; a.lam_x = c->gn_dct64.lam_x; a.lam_y = c->gn_dct64.lam_y; a.tb = &c->gn_tb;
+    a.x = cv.take(3 * P); a.r = cv.take(3 * P); a.p = cv.take(3 * P); a.s = cv.take(3 * P); a.wv = cv.take(3 * P);
+    a.gbar = cv.take(8); a.partials6 = cv.take(6 * 1184); a.partials3 = cv.take(3 * 592);
+    a.r32 = (float *)cv.take(n32); a.t1 = (float *)cv.take(n32); a.t2 = (float *)cv.take(n32); a.u32 = (float *)cv.take(n32);
+    a.state = c->gn_state; a.w = w; a.h = h; a.maxiter = max_it; a.alpha = alpha; a.lam = lambda; a.rtol = rtol;
+    launch_gn_coeffs(c->stream, w, h, d_f1, d_f2, alpha, lambda, fx, fy, dinv, b);
+    prof_begin(c, CAT_GN);
+    FOTO_TRY(gn_dct_begin(c->stream, a));
+    c->stats.launches += 4;
+    const int chunk = 8;
+    int launches = 0, done = 0, n_it = 0, inf = 0, enq = 0, nchunk = 0;
+    auto check = [&](int ci) -> int {
+        CUDA_TRY(cudaEventSynchronize(c->look_ev[ci % kLookSlots]));
+        gn_dct_read_state(c->h_gn_state + (ci % kLookSlots) * 256, &done, &n_it, &inf);
+        return FOTO_OK;
+    };
+    while (!done && enq < max_it) {
+        if (nchunk >= 2) FOTO_TRY(check(nchunk - 2));
+        if (done) break;
+        const int cnt = max_it - enq < chunk ? max_it - enq : chunk;
+        FOTO_TRY(gn_dct_enqueue_iterations(c->stream, a, enq, cnt, &launches));
+        CUDA_TRY(cudaMemcpyAsync(c->h_gn_state + (nchunk % kLookSlots) * 256, c->gn_state, gn_dct_state_bytes(), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaEventRecord(c->look_ev[nchunk % kLookSlots], c->stream));
+        enq += cnt; nchunk++;
+    }
+    for (int ci = nchunk - 2 < 0 ? 0 : nchunk - 2; ci < nchunk && !done; ci++) FOTO_TRY(check(ci));
+    if (!done) { set_error("spectral GN solve ended without a decision"); return FOTO_ERR_CUDA; }
+    gn_dct_copy_out(c->stream, a, d_u, d_v, d_m);
+    prof_end(c);
+    c->stats.launches += launches + 1; c->stats.gn_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    prof_resolve(c);
+    c->stats.gn_iterations += n_it;
+    c->stats.gn_pixels += (long long)n_it * (long long)P;
+    if (iters) *iters = n_it;
+    if (info) *info = inf;
+    return FOTO_OK;
+}
+
 extern "C" int foto_gn_solve_dev(foto_ctx *c, const double *d_f1, const double *d_f2, int w, int h, double alpha,
                                  double lambda, double rtol, int max_it, double *d_u, double *d_v, double *d_m,
                                  int *iters, int *info)
@@ -452,6 +539,10 @@ extern "C" int foto_gn_solve_dev(foto_ctx *c, const double *d_f1, const double *
     if (rtol <= 0) rtol = 1e-13;
     if (max_it <= 0) max_it = 20000;
     FOTO_TRY(ctx_bind(c));
+    // solver choice: 0 streaming Jacobi-PCG, 2 on-chip single-reduction Jacobi-PCG, 3 spectral preconditioner (TF32
+    // tensor-core DCT, fp64 recurrences), -1 auto = spectral from 64 x 64 pixels on, else on-chip / streaming
+    if (c->cg_variant == 3 || (c->cg_variant == -1 && P >= 4096 && w <= 4096 && h <= 4096))
+        return gn_solve_spectral(c, d_f1, d_f2, w, h, alpha, lambda, rtol, max_it, d_u, d_v, d_m, iters, info);
     FOTO_TRY(ensure(&c->ws, &c->ws_bytes, 2 * Carver::bytes(P) + 8 * Carver::bytes(3 * P)));
     Carver cv(c->ws);
     GnArgs a;
@@ -464,7 +555,6 @@ extern "C" int foto_gn_solve_dev(foto_ctx *c, const double *d_f1, const double *
     a.out = &c->d_res->cg_iters;
     launch_gn_coeffs(c->stream, w, h, d_f1, d_f2, alpha, lambda, fx, fy, dinv, b);
     prof_begin(c, CAT_GN);
-    // kernel choice as for the Poisson solve: 0 streaming, 2 on-chip single-reduction, -1 auto = on-chip when it fits
     const bool gnf_fits = gn_fused_fits(c->onchip, c->device, h, w);
     if (c->cg_variant == 2 && !gnf_fits) { set_error("image %dx%d does not fit the single-reduction on-chip GN variant", h, w); return FOTO_ERR_ARG; }
     if (c->cg_variant == 2 || (c->cg_variant == -1 && gnf_fits)) { FOTO_TRY(launch_gn_fused(c->stream, a, c->device, c->onchip)); c->stats.launches++; }
@@ -496,7 +586,7 @@ static int default_variant()
     if (v == -2) {
         const char *e = getenv("FOTO_CG_VARIANT");
         v = e ? atoi(e) : -1;
-        if (v < -1 || v > 2 || v == 1) v = -1;
+        if (v < -1 || v > 3 || v == 1) v = -1;
         g_default_variant.store(v);
     }
     return v;
@@ -504,7 +594,7 @@ static int default_variant()
 
 extern "C" int foto_set_default_cg_variant(int v)
 {
-    if (v < -1 || v > 2 || v == 1) { set_error("cg variant must be -1 (auto), 0 (streaming) or 2 (on-chip single-reduction)"); return FOTO_ERR_ARG; }
+    if (v < -1 || v > 3 || v == 1) { set_error("cg variant must be -1 (auto), 0 (streaming), 2 (on-chip single-reduction) or 3 (GN: spectral preconditioner)"); return FOTO_ERR_ARG; }
     g_default_variant.store(v);
     return FOTO_OK;
 }

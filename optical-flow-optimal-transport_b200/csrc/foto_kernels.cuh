@@ -132,6 +132,28 @@ struct GnArgs {
 };
 int gn_pcg_config(int device, int *grid, int *block);
 int launch_gn_pcg(cudaStream_t st, const GnArgs &a, int grid, int block);
+// spectral (DCT) preconditioner applied in TF32 on the tensor cores, fp64 Krylov recurrences (gn_dct.cu)
+struct GnDctTables {            // fp32 zero-padded DCT matrices, owned by the context, valid for (w, h)
+    int w = 0, h = 0, wp = 0, hp = 0;
+    float *base = nullptr, *Cx = nullptr, *CxT = nullptr, *Cy = nullptr, *CyT = nullptr;
+};
+struct GnDctArgs {
+    const double *fx, *fy, *f2, *b;         // P, P, P, 3P
+    const double *lam_x, *lam_y;            // eigenvalues of -lap1d (DctTables)
+    const GnDctTables *tb;
+    double *x, *r, *p, *s, *wv;             // 3P each
+    double *gbar, *partials6, *partials3;   // 8, 6 * 1184, 3 * 592
+    float *r32, *t1, *t2, *u32;             // 3 * hp * wp each
+    void *state;                            // gn_dct_state_bytes()
+    int w, h, maxiter;
+    double alpha, lam, rtol;
+};
+size_t gn_dct_state_bytes();
+int gn_dct_prepare_tables(cudaStream_t st, const DctTables &tb, int w, int h, GnDctTables &out);
+int gn_dct_begin(cudaStream_t st, const GnDctArgs &a);
+int gn_dct_enqueue_iterations(cudaStream_t st, const GnDctArgs &a, int it0, int count, int *launches);
+void gn_dct_copy_out(cudaStream_t st, const GnDctArgs &a, double *u, double *v, double *m);
+void gn_dct_read_state(const void *host_copy, int *done, int *iters, int *info);
 // on-chip resident, one grid all-reduce per iteration (gn_fused.cu): uses fx, fy, f2, dinv, b, x, out, sync.error only
 bool gn_fused_fits(OnchipScratch &s, int device, int h, int w);
 int launch_gn_fused(cudaStream_t st, const GnArgs &a, int device, OnchipScratch &s);

@@ -98,8 +98,9 @@ def _check(rc):
 
 
 def set_default_cg_variant(variant):
-    """-1 auto (the on-chip single-reduction kernel when the grid fits, else streaming), 0 streaming (textbook CG
-    recurrences), 2 on-chip single-reduction.  Applies to the Poisson and the GN solve."""
+    """-1 auto, 0 streaming (textbook CG recurrences), 2 on-chip single-reduction, 3 GN only: fp64 CG with the spectral
+    (DCT) preconditioner on the tensor cores.  Auto: Poisson solve on-chip when the grid fits, else streaming; GN solve
+    spectral from 64 x 64 pixels on, else on-chip / streaming Jacobi-PCG."""
     _check(lib().foto_set_default_cg_variant(int(variant)))
 
 

@@ -8,10 +8,10 @@ restatement of the reference, pinned to the reference's own outputs by tests/tes
                                       pixel, and (sum, sum|.|, max|.|, l2) of each full field
     tests/golden/bench_seeds_oracle.npz   the same for the bench pairs
 
-    python tools/parity_config3.py [--procs 7] [--only config3|bench]
+    python tests/golden/make_config3_oracle.py [--procs 7] [--only config3|bench]
 """
 import argparse, multiprocessing as mp, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "optical-flow-optimal-transport_b200"))
 import numpy as np
 from foto_b200 import synth

@@ -2,7 +2,7 @@
 
   * the 64 pairs of BASELINE.json config 3 (8 Middlebury-shape sequences x 8 illumination perturbations,
     foto_b200.synth.config3_pairs) against the CPU oracle's results (tests/golden/config3_oracle.npz, written by
-    tools/parity_config3.py): outer-iteration count and every CG iteration count equal, u / v / m within 1e-9 relative
+    tests/golden/make_config3_oracle.py): outer-iteration count and every CG iteration count equal, u / v / m within 1e-9 relative
     on the stored sample and on whole-field sums;
   * the 32 pairs bench.py times (8 ranks x 4 seeds; tests/golden/bench_seeds_oracle.npz), same bar;
   * one pair per config-3 shape that config 1 does not cover, against goldens recorded from the UNMODIFIED reference
@@ -26,7 +26,7 @@ def _golden_or_skip(name):
     try:
         return load_golden(name)
     except FileNotFoundError:
-        pytest.skip(f"tests/golden/{name}.npz not generated yet (tools/parity_config3.py)")
+        pytest.skip(f"tests/golden/{name}.npz not generated yet (tests/golden/make_config3_oracle.py)")
 
 
 def _stats(a):
