@@ -150,6 +150,10 @@ int  foto_dct_xy_dev(foto_ctx *ctx, const double *d_in, double *d_out, double *d
                      int Ny, int Nx, int inverse);
 int  foto_dct_t_solve_dev(foto_ctx *ctx, const double *d_in, double *d_out, int gNt, int Ny, int Nx, int y_off,
                           int ny_loc, double r, double eps);
+/* t-slab <-> y-slab transpose of the DCT all-to-all in one pass: direction 0 packs nloc planes [nloc][Ny][Nx] into the
+ * send buffer whose block for rank g ([nloc][rows of g][Nx], rows of g = [g Ny/world, (g+1) Ny/world)) is contiguous;
+ * direction 1 unpacks a received buffer of that layout into planes */
+int  foto_slab_pack_dev(foto_ctx *ctx, int direction, int nloc, int Ny, int Nx, int world, const double *d_in, double *d_out);
 /* K4 on device buffers: utils.opticalflow_from_benamoubrenier, utils.py:148 */
 int  foto_flow_dev(foto_ctx *ctx, const double *d_phi, int Nt, int Nx, int Ny, double *d_u, double *d_v, double *d_m);
 

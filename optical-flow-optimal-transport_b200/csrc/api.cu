@@ -1101,6 +1101,19 @@ extern "C" int foto_dct_t_solve_dev(foto_ctx *c, const double *in, double *out, 
     return FOTO_OK;
 }
 
+// t-slab <-> y-slab transpose buffers of the DCT all-to-all: direction 0 packs nloc planes [nloc][Ny][Nx] into the send
+// buffer (block for rank g contiguous: [nloc][rows of g][Nx]), direction 1 unpacks a received buffer into planes
+extern "C" int foto_slab_pack_dev(foto_ctx *c, int direction, int nloc, int Ny, int Nx, int world, const double *d_in, double *d_out)
+{
+    if (!c || !d_in || !d_out || nloc < 1 || Ny < world || world < 1 || Nx < 1) { set_error("foto_slab_pack_dev: bad argument"); return FOTO_ERR_ARG; }
+    FOTO_TRY(ctx_bind(c));
+    if (direction == 0) launch_slab_pack(c->stream, nloc, Ny, Nx, world, d_in, d_out, nullptr, nullptr);
+    else launch_slab_pack(c->stream, nloc, Ny, Nx, world, nullptr, nullptr, d_out, d_in);
+    c->stats.launches++;
+    CUDA_TRY(cudaGetLastError());
+    return FOTO_OK;
+}
+
 extern "C" int foto_flow_dev(foto_ctx *c, const double *d_phi, int Nt, int Nx, int Ny, double *d_u, double *d_v, double *d_m)
 {
     if (!c || !d_phi || !d_u || !d_v || !d_m) { set_error("foto_flow_dev: NULL argument"); return FOTO_ERR_ARG; }

@@ -461,7 +461,36 @@ __global__ void __launch_bounds__(256) k_sum1(const double *__restrict__ partial
     if (threadIdx.x == 0) out1[0] = acc[0];
 }
 
+// Time-slab transpose, one pass: element (l, y, x) of this rank's L planes sits at
+//   off_g * L * Nx + (l * rows_g + (y - y0_g)) * Nx + x,   g = owner of row y, y0_g = g Ny / world (slab.split),
+// in the all-to-all buffer, i.e. the block sent to / received from rank g is contiguous.  pack: planes -> buffer;
+// unpack: buffer -> planes.
+__global__ void __launch_bounds__(256) k_slab_pack(int L, int Ny, int Nx, int world, const double *__restrict__ pin,
+                                                    double *__restrict__ bout, double *__restrict__ pout, const double *__restrict__ bin)
+{
+    const size_t total = (size_t)L * Ny * Nx, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride) {
+        const int x = (int)(k % Nx);
+        const size_t ly = k / Nx;
+        const int y = (int)(ly % Ny), l = (int)(ly / Ny);
+        int g = (int)(((long long)(y + 1) * world - 1) / Ny);          // owner of row y: g Ny / world <= y < (g+1) Ny / world
+        while ((long long)g * Ny / world > y) g--;
+        while ((long long)(g + 1) * Ny / world <= y) g++;
+        const int y0 = (int)((long long)g * Ny / world), rows = (int)((long long)(g + 1) * Ny / world) - y0;
+        const size_t b = ((size_t)y0 * L + (size_t)l * rows + (size_t)(y - y0)) * Nx + x;
+        if (pin) bout[b] = pin[k]; else pout[k] = bin[b];
+    }
+}
+
 }  // namespace
+
+void launch_slab_pack(cudaStream_t st, int L, int Ny, int Nx, int world, const double *planes_in, double *buf_out,
+                      double *planes_out, const double *buf_in)
+{
+    const size_t total = (size_t)L * Ny * Nx;
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    k_slab_pack<<<blocks, 256, 0, st>>>(L, Ny, Nx, world, planes_in, buf_out, planes_out, buf_in);
+}
 
 void launch_ingest_u8(cudaStream_t st, unsigned int n, const unsigned char *in, double *out)
 {

@@ -58,6 +58,9 @@ void launch_pack_flo(cudaStream_t st, unsigned int n, const double *u, const dou
 void launch_flow_metrics(cudaStream_t st, unsigned int n, const double *u, const double *v, const double *ug,
                          const double *vg, double *partials, double *out6);
 void launch_ingest_u8(cudaStream_t st, unsigned int n, const unsigned char *in, double *out);
+// time-slab transpose: [L][Ny][Nx] planes <-> all-to-all buffer [rank g][L][rows of g][Nx] (rows split like slab.split)
+void launch_slab_pack(cudaStream_t st, int L, int Ny, int Nx, int world, const double *planes_in, double *buf_out,
+                      double *planes_out, const double *buf_in);
 // sum (255 a - 255 b)^2 (utils.IE, utils.py:354); partials: >= 1184 doubles
 void launch_ie_sumsq(cudaStream_t st, unsigned int n, const double *a, const double *b, double *partials, double *out1);
 // generic tridiagonal-along-one-axis apply used by foto_op_apply

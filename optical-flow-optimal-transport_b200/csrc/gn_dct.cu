@@ -30,14 +30,13 @@ namespace foto {
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 32, GT = 128;
-constexpr int APITCH = BK + 4, BPITCH = BN + 8;          // bank-conflict-free fragment loads (see comments below)
-
 struct GnDctState {             // device
     double gam_old[2], alpha_old[2], d_old[2];  // double buffered by iteration parity
     double stop2;
     int done, iters, info, pad;
 };
+
+constexpr int BK = 32, APITCH = BK + 4;                   // A fragment loads hit bank 4g + t: conflict free
 
 __device__ __forceinline__ void cp_async16(float *dst, const float *src, bool valid)
 {
@@ -55,40 +54,46 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned int (&a)[
 
 // C[b] = A[b] * B[b], fp32 row-major, TF32 tensor-core MMA with fp32 accumulation.  All leading dimensions, K and the
 // base pointers are multiples of 4 floats (the buffers are padded), so tiles travel with 16-byte cp.async; rows / columns
-// beyond M / N are zero-filled and not stored.  4 warps, each a 32 x 32 output tile (2 x 4 m16n8 fragments).
-__global__ void __launch_bounds__(GT) k_sgemm_tf32(int M, int N, int K, const float *__restrict__ A, int lda, long long strideA,
-                                                    const float *__restrict__ B, int ldb, long long strideB,
-                                                    float *__restrict__ C, int ldc, long long strideC, const int *skip)
+// beyond M / N are zero-filled and not stored.  Block tile BM x BN, warp tile WM x WN (m16n8 fragments), STAGES-deep
+// cp.async ring.  The transforms of one image are small (0.8 GFLOP) and their operands live in L2: with 64 x 64 tiles
+// the kernel re-reads 51 MB per GEMM and runs at the L2 bandwidth (15 us, 3.4 TB/s, ncu); 128-wide tiles halve that.
+template <int BM, int BN, int WM, int WN, int STAGES>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) k_sgemm_tf32(int M, int N, int K, const float *__restrict__ A, int lda,
+                                                                          long long strideA, const float *__restrict__ B, int ldb,
+                                                                          long long strideB, float *__restrict__ C, int ldc,
+                                                                          long long strideC, const int *skip)
 {
-    __shared__ __align__(16) float As[2][BM][APITCH];   // As[m][k]
-    __shared__ __align__(16) float Bs[2][BK][BPITCH];   // Bs[k][n]
+    constexpr int GT = (BM / WM) * (BN / WN) * 32, BPITCH = BN + 8;      // B fragment loads hit bank 8t + g: conflict free
+    constexpr int MI = WM / 16, NJ = WN / 8;
+    extern __shared__ __align__(16) float gsm[];
+    float (*As)[BM][APITCH] = reinterpret_cast<float (*)[BM][APITCH]>(gsm);                           // As[stage][m][k]
+    float (*Bs)[BK][BPITCH] = reinterpret_cast<float (*)[BK][BPITCH]>(gsm + STAGES * BM * APITCH);    // Bs[stage][k][n]
     if (skip && *skip) return;
     A += (size_t)blockIdx.z * strideA; B += (size_t)blockIdx.z * strideB; C += (size_t)blockIdx.z * strideC;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int wm = (warp / (BN / WN)) * WM, wn = (warp % (BN / WN)) * WN;
     const int g = lane >> 2, t = lane & 3;
-    float acc[2][4][4];
+    float acc[MI][NJ][4];
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < MI; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+        for (int j = 0; j < NJ; j++)
 #pragma unroll
             for (int e = 0; e < 4; e++) acc[i][j][e] = 0.f;
 
-    // A tile 64 x 32 floats = 512 16-byte chunks: 4 passes of (row = pass*16 + tid/8, k4 = tid%8);
-    // B tile 32 x 64 floats = 512 chunks: 4 passes of (row = pass*8 + tid/16, n4 = tid%16)
+    // A tile BM x 32 floats: 8 16-byte chunks per row; B tile 32 x BN floats: BN/4 chunks per row
     auto prefetch = [&](int stage, int k0) {
 #pragma unroll
-        for (int ps = 0; ps < 4; ps++) {
-            const int r = ps * 16 + (tid >> 3), c = (tid & 7) * 4;
+        for (int ps = 0; ps < BM * 8 / GT; ps++) {
+            const int idx = ps * GT + tid, r = idx >> 3, c = (idx & 7) * 4;
             const int gm = m0 + r, gk = k0 + c;
             const bool ok = gm < M && gk < K;
             cp_async16(&As[stage][r][c], ok ? A + (size_t)gm * lda + gk : A, ok);
         }
 #pragma unroll
-        for (int ps = 0; ps < 4; ps++) {
-            const int r = ps * 8 + (tid >> 4), c = (tid & 15) * 4;
+        for (int ps = 0; ps < BK * (BN / 4) / GT; ps++) {
+            const int idx = ps * GT + tid, r = idx / (BN / 4), c = (idx % (BN / 4)) * 4;
             const int gk = k0 + r, gn = n0 + c;
             const bool ok = gk < K && gn < N;
             cp_async16(&Bs[stage][r][c], ok ? B + (size_t)gk * ldb + gn : B, ok);
@@ -96,40 +101,43 @@ __global__ void __launch_bounds__(GT) k_sgemm_tf32(int M, int N, int K, const fl
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     const int nk = (K + BK - 1) / BK;
-    prefetch(0, 0);
+#pragma unroll
+    for (int s0 = 0; s0 < STAGES - 1; s0++) {
+        if (s0 < nk) prefetch(s0, s0 * BK); else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     for (int kt = 0; kt < nk; kt++) {
-        const int st = kt & 1;
-        if (kt + 1 < nk) prefetch(st ^ 1, (kt + 1) * BK); else asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncthreads();
+        const int st = kt % STAGES;
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");     // k-tile kt has landed
+        __syncthreads();                                                          // ... and stage (kt-1) % STAGES is free
+        if (kt + STAGES - 1 < nk) prefetch((kt + STAGES - 1) % STAGES, (kt + STAGES - 1) * BK);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll
         for (int k8 = 0; k8 < BK; k8 += 8) {
-            unsigned int a[2][4], b[4][2];
-            // A fragment (16 x 8, row major): a0 (g, t), a1 (g+8, t), a2 (g, t+4), a3 (g+8, t+4); pitch 36: bank 4g + t
+            unsigned int a[MI][4], b[NJ][2];
+            // A fragment (16 x 8, row major): a0 (g, t), a1 (g+8, t), a2 (g, t+4), a3 (g+8, t+4)
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
+            for (int i = 0; i < MI; i++) {
                 const float *p = &As[st][wm + i * 16 + g][k8 + t];
                 a[i][0] = __float_as_uint(p[0]); a[i][1] = __float_as_uint(p[8 * APITCH]);
                 a[i][2] = __float_as_uint(p[4]); a[i][3] = __float_as_uint(p[8 * APITCH + 4]);
             }
-            // B fragment (8 x 8, column major): b0 (k = t, n = g), b1 (k = t+4, n = g); pitch 72: bank 8t + g
+            // B fragment (8 x 8, column major): b0 (k = t, n = g), b1 (k = t+4, n = g)
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < NJ; j++) {
                 const float *p = &Bs[st][k8 + t][wn + j * 8 + g];
                 b[j][0] = __float_as_uint(p[0]); b[j][1] = __float_as_uint(p[4 * BPITCH]);
             }
 #pragma unroll
-            for (int i = 0; i < 2; i++)
+            for (int i = 0; i < MI; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) mma_tf32(acc[i][j], a[i], b[j]);
+                for (int j = 0; j < NJ; j++) mma_tf32(acc[i][j], a[i], b[j]);
         }
-        __syncthreads();
     }
     // C fragment: c0 (g, 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < MI; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < NJ; j++) {
             const int gn = n0 + wn + j * 8 + 2 * t;
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
@@ -139,6 +147,22 @@ __global__ void __launch_bounds__(GT) k_sgemm_tf32(int M, int N, int K, const fl
             }
         }
 }
+
+template <int BM, int BN, int WM, int WN, int STAGES>
+struct GemmCfg {
+    static constexpr int smem = STAGES * (BM * APITCH + BK * (BN + 8)) * (int)sizeof(float);
+    static constexpr int threads = (BM / WM) * (BN / WN) * 32;
+    static void launch(cudaStream_t st, int M, int N, int K, const float *A, int lda, long long sA, const float *B, int ldb, long long sB,
+                       float *C, int ldc, long long sC, int batch, const int *skip)
+    {
+        dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch);
+        k_sgemm_tf32<BM, BN, WM, WN, STAGES><<<grid, threads, smem, st>>>(M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, skip);
+    }
+    static cudaError_t prepare() { return cudaFuncSetAttribute(k_sgemm_tf32<BM, BN, WM, WN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
+};
+using GemmSmall = GemmCfg<64, 64, 32, 32, 4>;       // 128 threads, 74 KB
+using GemmWide = GemmCfg<128, 128, 64, 32, 3>;      // 256 threads, 107 KB
+using GemmTall = GemmCfg<128, 64, 32, 32, 3>;       // 256 threads, 81 KB
 
 // fp64 n x n matrix -> fp32 np x np, zero padded
 __global__ void k_pad_matrix(int n, int np, const double *__restrict__ in, float *__restrict__ out)
@@ -211,7 +235,11 @@ __global__ void __launch_bounds__(256) k_spectral(int w, int h, int wp, int hp, 
     if (k >= P) return;
     const int a = (int)(k / (unsigned int)w), b = (int)(k - (unsigned int)a * w);
     const double mu = lam_y[a] + lam_x[b];
-    const double m00 = alpha * mu + gbar[0], m01 = gbar[1], m02 = gbar[2], m11 = alpha * mu + gbar[3], m12 = gbar[4], m22 = lam * mu + gbar[5];
+    // Gbar is only positive semi-definite (fx = fy = 0 on a 2 x 2 image; a constant frame): a relative 1e-6 shift keeps
+    // M positive definite at mu = 0 and is far below the accuracy a preconditioner needs
+    const double reg = 1e-6 * (gbar[0] + gbar[3] + gbar[5]) + 1e-300;
+    const double m00 = alpha * mu + gbar[0] + reg, m01 = gbar[1], m02 = gbar[2], m11 = alpha * mu + gbar[3] + reg, m12 = gbar[4],
+                 m22 = lam * mu + gbar[5] + reg;
     const size_t i0 = ((size_t)a) * wp + b, cs = (size_t)hp * wp;
     const double r0 = T[i0], r1 = T[cs + i0], r2 = T[2 * cs + i0];
     // adjugate of the symmetric 3 x 3 matrix
@@ -330,11 +358,23 @@ __global__ void __launch_bounds__(256) k_copy_out(unsigned int n, const double *
     if (k < P) { u[k] = x[k]; v[k] = x[P + k]; m[k] = x[2u * P + k]; }
 }
 
+// tile choice: FOTO_GN_TILE = 0 (64 x 64, default), 1 (128 x 128), 2 (128 x 64).  Measured at 388x584 (B200, us per GEMM,
+// X / Y transform): 64x64 15.0 / 11.1, 128x128 22.7 / 16.4, 128x64 slower than 64x64 too: the legacy mma.sync TF32 path
+// delivers ~450 FLOP/clk/SM here, so fewer, larger CTAs (50 on 148 SMs) lose more than the halved L2 traffic gains.
+int tile_mode(int, int)
+{
+    static int forced = -2;
+    if (forced == -2) { const char *e = getenv("FOTO_GN_TILE"); forced = e ? atoi(e) : -1; }
+    return forced >= 0 ? forced : 0;
+}
 void gemm(cudaStream_t st, int M, int N, int K, const float *A, int lda, long long sA, const float *B, int ldb, long long sB,
           float *C, int ldc, long long sC, int batch, const int *skip)
 {
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch);
-    k_sgemm_tf32<<<grid, GT, 0, st>>>(M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, skip);
+    switch (tile_mode(M, N)) {
+    case 1: GemmWide::launch(st, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch, skip); break;
+    case 2: GemmTall::launch(st, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch, skip); break;
+    default: GemmSmall::launch(st, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch, skip); break;
+    }
 }
 
 }  // namespace
@@ -355,6 +395,7 @@ int gn_dct_prepare_tables(cudaStream_t st, const DctTables &tb, int w, int h, Gn
     k_pad_matrix<<<(unsigned int)((ny + 255) / 256), 256, 0, st>>>(h, hp, tb.Cy, out.Cy);
     k_pad_matrix<<<(unsigned int)((ny + 255) / 256), 256, 0, st>>>(h, hp, tb.CyT, out.CyT);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(GemmSmall::prepare()); CUDA_TRY(GemmWide::prepare()); CUDA_TRY(GemmTall::prepare());       // per device: tables are per context
     out.w = w; out.h = h; out.wp = wp; out.hp = hp;
     return FOTO_OK;
 }

@@ -28,7 +28,7 @@ EXPORTS = [
     "foto_solve_batch", "foto_gn_solve_batch", "foto_pack_flo", "foto_flow_metrics",
     "foto_ctx_set_stream", "foto_slab_rhs_dev", "foto_slab_prox_dev", "foto_dct_xy_dev", "foto_dct_t_solve_dev",
     "foto_flow_dev", "foto_ingest_u8_dev", "foto_pack_flo_dev", "foto_flow_metrics_dev", "foto_warp_dev",
-    "foto_solve_batch_u8",
+    "foto_solve_batch_u8", "foto_slab_pack_dev",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -394,6 +394,10 @@ class Context:
         vp = C.c_void_p
         _check(lib().foto_dct_t_solve_dev(self._h, vp(d_in), vp(d_out), int(gNt), int(Ny), int(Nx), int(y_off), int(ny_loc),
                                           _d(r), _d(eps)))
+
+    def slab_pack(self, direction, nloc, Ny, Nx, world, d_in, d_out):
+        vp = C.c_void_p
+        _check(lib().foto_slab_pack_dev(self._h, int(direction), int(nloc), int(Ny), int(Nx), int(world), vp(d_in), vp(d_out)))
 
     def flow_dev(self, d_phi, Nt, Nx, Ny, d_u, d_v, d_m):
         vp = C.c_void_p

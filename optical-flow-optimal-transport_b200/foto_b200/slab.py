@@ -61,6 +61,7 @@ class SlabSolver:
         self.tmp = torch.empty((L, P), **f64)
         self.B = torch.empty((self.Nt, self.nyl * self.Nx), **f64)   # spectrum, y-slab layout
         self.B2 = torch.empty_like(self.B)
+        self.xbuf = torch.empty(L * P, **f64)                 # all-to-all staging: block of rank g = [L][rows of g][Nx]
         self.sums = torch.zeros(2, **f64)
         self.cs = (L + 2) * P
 
@@ -89,10 +90,10 @@ class SlabSolver:
         if self.world == 1:
             B.view(self.Nt, self.Ny, self.Nx).copy_(A3)
             return
-        send = torch.cat([A3[:, y0:y1, :].reshape(-1) for (y0, y1) in self.geom["y"]])
+        self.ctx.slab_pack(0, self.nloc, self.Ny, self.Nx, self.world, A.data_ptr(), self.xbuf.data_ptr())   # one gather kernel
         in_split = [self.nloc * (y1 - y0) * self.Nx for (y0, y1) in self.geom["y"]]
         out_split = [(n1 - n0) * self.nyl * self.Nx for (n0, n1) in self.geom["t"]]
-        dist.all_to_all_single(B.view(-1), send, out_split, in_split)        # rank order = plane order
+        dist.all_to_all_single(B.view(-1), self.xbuf, out_split, in_split)   # rank order = plane order
 
     def _to_t_slabs(self, B, A):
         """B: [Nt, nyl, Nx] -> A: [L, Ny, Nx]."""
@@ -102,13 +103,8 @@ class SlabSolver:
             return
         in_split = [(n1 - n0) * self.nyl * self.Nx for (n0, n1) in self.geom["t"]]      # contiguous plane ranges of B
         out_split = [self.nloc * (y1 - y0) * self.Nx for (y0, y1) in self.geom["y"]]
-        recv = torch.empty(sum(out_split), dtype=torch.float64, device=self.dev)
-        dist.all_to_all_single(recv, B.view(-1), out_split, in_split)
-        A3 = A.view(self.nloc, self.Ny, self.Nx)
-        off = 0
-        for (y0, y1), n in zip(self.geom["y"], out_split):
-            A3[:, y0:y1, :] = recv[off:off + n].view(self.nloc, y1 - y0, self.Nx)
-            off += n
+        dist.all_to_all_single(self.xbuf, B.view(-1), out_split, in_split)
+        self.ctx.slab_pack(1, self.nloc, self.Ny, self.Nx, self.world, self.xbuf.data_ptr(), A.data_ptr())   # one scatter kernel
 
     # ------------------------------------------------------------------ solve
     def solve(self, rho0, rhoT, r=1.0, convergence_tol=0.3, reg_epsilon=1e-3, max_it=100):
