@@ -1,4 +1,5 @@
-// cg_fused.cu -- K2a, on-chip resident CG with ONE grid all-reduce per iteration.
+// cg_fused.cu -- K2a, on-chip resident CG with ONE grid all-reduce per iteration and NOTHING ELSE on the critical path
+// between two stencils but the all-reduce and the vector update.
 //
 // The textbook recurrences (scipy's, benamou_brenier.py:85; cg_kernels.cu) need two grid all-reduces per iteration
 // (p.Ap, then r.r); an on-chip kernel built that way (round 1, removed) spent 8 800 of its 16 200 cycles per
@@ -14,20 +15,27 @@
 // a recurrence instead of being recomputed.  Measured against scipy's cg on the reference's systems (CPU prototype,
 // 4 grids up to 388x584x4): identical iteration counts in every outer iteration, phi within 9e-11 of scipy's per
 // solve and u, v, m within 8e-12 after the full ALG2 loop (contract: 1e-9).  The parity tests run this kernel as
-// the default and the textbook kernels beside it.
+// the default and the streaming textbook kernel beside it.
 //
-// The stencil now acts on r, so r (not p) lives in shared memory with the halo ring; p and s live in registers, x and
-// w in private shared-memory slots.  Tile-edge values of the new r go through L2 to the four neighbours without any
-// barrier or fence: every exported word carries the parity of its generation in the least significant mantissa bit
-// (the owner keeps the same rounded value, so both copies of r agree; the perturbation is one ulp of an edge value
-// per iteration, the size of an ordinary rounding error), and the reader spins on each word until the parity is
-// the one it expects (table-driven export pass after the update, mirror of the import).  One buffer is enough: a CTA
-// overwrites generation g with g+1 only after the all-reduce of iteration g, which every neighbour enters after it
-// has read generation g.  (Measured alternatives: flag + release
-// fence hand-off 2 900 cycles per iteration, as much as the grid barrier it replaces; sentinel reset + triple
-// buffering doubles the stores and costs 3 000 cycles in the reset loop; exporting from registers inside the unrolled
-// update costs the edge warps 1 500 cycles.)  Half of the x update of iteration k covers the L2 hop of the edge
-// values, the other half runs in the shadow of the all-reduce of iteration k+1.
+// The stencil acts on r, so r lives in shared memory with a one-cell halo ring; p and s live in registers, x and w in
+// private shared-memory slots.  Tile-edge exchange (round 2, second form): what crosses L2 is the tile edge of
+// w = A r, NOT of the new r.  w is known before the all-reduce, so its L2 hop (~1 000-1 400 cycles store -> visible)
+// runs in the shadow of the all-reduce instead of after the update (the first form exported r after the update and
+// spun ~1 000 cycles per iteration at the top of the next one).  Each CTA keeps, for the halo ring, its own copies of
+// r (in the ring of rs) and s (registers) and advances them with the owner's arithmetic -- s = s beta + w,
+// r = r - alpha s, separately rounded products and sums, the same alpha and beta -- so both copies stay bit-identical.
+// The ring of r_0 = b is read from global memory at setup.
+// No barrier and no fence order the exchange: every exported word carries a generation tag in the least significant
+// mantissa bit (the owner writes the same rounded w back into its slot, so both sides use one value; the perturbation
+// is one ulp of an edge value of w per iteration, the size of an ordinary rounding error) and the reader spins on
+// each word until the tag is the one it expects.  Edge words are double buffered on the iteration parity, tag =
+// bit 1 of the iteration number: a CTA overwrites buffer (k & 1) with generation k+2 only after the all-reduce of
+// iteration k+1, which every neighbour enters after it has consumed generation k.
+// (Measured alternatives: flag + release fence hand-off 2 900 cycles per iteration, as much as the grid barrier it
+// replaces; sentinel reset + triple buffering doubles the stores and costs 3 000 cycles in the reset loop; exporting
+// from registers inside the unrolled update costs the edge warps 1 500 cycles.)
+// Shadow of the all-reduce of iteration k: export of w_k's edges, the whole x += alpha_{k-1} p_{k-1}, import of the
+// neighbours' edges into registers.
 #include "foto_kernels.cuh"
 #include "grid_sync.cuh"
 
@@ -39,12 +47,19 @@ using namespace gsync;
 
 struct Geom {
     int gy, gx, maxlen;
-    double *edges;                 // [ncta][4 (N,S,W,E)][NT * maxlen] tile-edge values of r, LSB = generation parity
+    double *edges;                 // [2 (iteration parity)][ncta][4 (N,S,W,E)][NT * maxlen] tile-edge values of w, LSB = tag
     unsigned long long *slots;     // all-reduce slots (grid_sync.cuh)
     long long *prof;
 };
 
 constexpr int kHaloPerThread = 4;
+
+// x[k] += v at the L2 (one adder per address and iteration: deterministic; IEEE addition, i.e. the value a load, an add
+// and a store would give, without the round trip and with half the traffic)
+__device__ __forceinline__ void red_add_f64(double *p, double v)
+{
+    asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
 
 // XG: x lives in global memory (L2 resident) instead of shared memory: the large variant (384 threads x 24 cell slots =
 // 9 216; 3 warps per SM sub-partition leave a thread 168 registers) for grids such as 480x640x4 whose x slots no
@@ -62,71 +77,71 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
     const int x0 = (int)((long long)bx * Nx / g.gx), x1 = (int)((long long)(bx + 1) * Nx / g.gx);
     const int ty = y1 - y0, tx = x1 - x0, PX = tx + 2, PY = ty + 2, plane = PY * PX;
     const int psz = (NT * plane + 1) & ~1;
-    double *rs = smem;                                  // [NT][PY][PX]  r, halo ring (zero outside the domain)
+    // layout: scratch and the small tables first (constant offsets), then r, x, w, then the per-entry halo state
+    double *red = smem;                                 // reduction scratch: 64 block_sum, 64..67 totals / flags, 72..77 profile
+    double *dtab = red + 80;                            // diagonal entries for 3..6 neighbours
+    double *rs = dtab + 4;                              // [NT][PY][PX]  r, halo ring (zero outside the domain)
     double *xs = rs + psz;                              // [CPT][NTHREADS] x
     double *ws = xs + (XG ? 0 : CPT * NTHREADS);        // [CPT][NTHREADS] w = A r
-    double *red = ws + CPT * NTHREADS;                  // reduction scratch: 64 block_sum, 64..66 totals, 72..77 profile
-    double *dtab = red + 80;                            // diagonal entries for 3..6 neighbours
-    int *hsrc = (int *)(dtab + 4);                      // halo import table: offset into g.edges
-    int *hdst = hsrc + 2 * NT * (tx + ty);              //                    index into rs
-    int *esrc = hdst + 2 * NT * (tx + ty);              // edge export table: index into rs
-    int *edst = esrc + 2 * NT * (tx + ty);              //                    offset into my_edges
+    double *shs = ws + CPT * NTHREADS;                  // s on the halo-ring cells (copy of the neighbours' s), by entry
+    // one table entry per exchanged edge cell (import and export lists have the same sides and lengths):
+    //   .x offset of the neighbour's word in a parity buffer of g.edges   .y ring cell of rs it feeds
+    //   .z slot of ws (of the owning thread) that is exported              .w offset of the exported word in my_edges
+    int4 *htab = (int4 *)(shs + 2 * NT * (tx + ty));
     const bool hasN = by > 0, hasS = by < g.gy - 1, hasW = bx > 0, hasE = bx < g.gx - 1;
     const double off = -a.rcoef * 1.0;
     const int edge_stride = NT * g.maxlen;
+    const size_t ebuf = (size_t)ncta * 4 * edge_stride;           // one parity buffer
     double *my_edges = g.edges + (size_t)cta * 4 * edge_stride;
     const int lx = tid % tx, r0 = tid / tx, RPP = NTHREADS / tx;
+    // warp 0 of every CTA owns the all-reduce (block total, arrive, root duty in CTA 0, poll of the totals) and takes no
+    // export / import entries, so that its poll starts long before the totals can arrive
+    constexpr int eoff = 32, estride = NTHREADS - eoff;
+    const int etid = tid - eoff;
 
     // ---- setup
     for (int i = tid; i < psz; i += NTHREADS) rs[i] = 0.0;
     if (tid < 4) dtab[tid] = -a.rcoef * (-(double)(tid + 3)) + a.rcoef * a.eps * 1.0;    // -r*L_ii + r*eps
+    __syncthreads();                                     // rs zeroed before the ring and the owners fill it
+    // ws slot of the tile cell (t, ly, lx): owner thread (ly / YPT) * tx + lx, slot t * YPT + ly % YPT
+    auto wslot = [&](int t, int ly, int lxx) { return (t * YPT + ly % YPT) * NTHREADS + (ly / YPT) * tx + lxx; };
     int nhalo = 0;
     {
         const int segNS = NT * tx, segWE = NT * ty;
+        // per side: e -> (t, pos); import from the neighbour's facing edge list, ring cell of rs, ring value of r_0 = b
+        // from global memory; export of the own edge row / column
         for (int e = tid; e < segNS; e += NTHREADS) {
             const int t = e / tx, pos = e - t * tx;
-            if (hasN) { hsrc[nhalo + e] = ((cta - g.gx) * 4 + 1) * edge_stride + e; hdst[nhalo + e] = (t * PY) * PX + pos + 1; }
+            if (hasN) {
+                htab[nhalo + e] = make_int4(((cta - g.gx) * 4 + 1) * edge_stride + e, (t * PY) * PX + pos + 1, wslot(t, 0, pos), 0 * edge_stride + e);
+                rs[(t * PY) * PX + pos + 1] = a.b[((size_t)t * Ny + (y0 - 1)) * Nx + (x0 + pos)];
+            }
         }
         if (hasN) nhalo += segNS;
         for (int e = tid; e < segNS; e += NTHREADS) {
             const int t = e / tx, pos = e - t * tx;
-            if (hasS) { hsrc[nhalo + e] = ((cta + g.gx) * 4 + 0) * edge_stride + e; hdst[nhalo + e] = (t * PY + ty + 1) * PX + pos + 1; }
+            if (hasS) {
+                htab[nhalo + e] = make_int4(((cta + g.gx) * 4 + 0) * edge_stride + e, (t * PY + ty + 1) * PX + pos + 1, wslot(t, ty - 1, pos), 1 * edge_stride + e);
+                rs[(t * PY + ty + 1) * PX + pos + 1] = a.b[((size_t)t * Ny + y1) * Nx + (x0 + pos)];
+            }
         }
         if (hasS) nhalo += segNS;
         for (int e = tid; e < segWE; e += NTHREADS) {
             const int t = e / ty, pos = e - t * ty;
-            if (hasW) { hsrc[nhalo + e] = ((cta - 1) * 4 + 3) * edge_stride + e; hdst[nhalo + e] = (t * PY + pos + 1) * PX; }
+            if (hasW) {
+                htab[nhalo + e] = make_int4(((cta - 1) * 4 + 3) * edge_stride + e, (t * PY + pos + 1) * PX, wslot(t, pos, 0), 2 * edge_stride + e);
+                rs[(t * PY + pos + 1) * PX] = a.b[((size_t)t * Ny + (y0 + pos)) * Nx + (x0 - 1)];
+            }
         }
         if (hasW) nhalo += segWE;
         for (int e = tid; e < segWE; e += NTHREADS) {
             const int t = e / ty, pos = e - t * ty;
-            if (hasE) { hsrc[nhalo + e] = ((cta + 1) * 4 + 2) * edge_stride + e; hdst[nhalo + e] = (t * PY + pos + 1) * PX + tx + 1; }
+            if (hasE) {
+                htab[nhalo + e] = make_int4(((cta + 1) * 4 + 2) * edge_stride + e, (t * PY + pos + 1) * PX + tx + 1, wslot(t, pos, tx - 1), 3 * edge_stride + e);
+                rs[(t * PY + pos + 1) * PX + tx + 1] = a.b[((size_t)t * Ny + (y0 + pos)) * Nx + x1];
+            }
         }
         if (hasE) nhalo += segWE;
-    }
-    int nexp = 0;
-    {
-        const int segNS = NT * tx, segWE = NT * ty;
-        for (int e = tid; e < segNS; e += NTHREADS) {
-            const int t = e / tx, pos = e - t * tx;
-            if (hasN) { esrc[nexp + e] = (t * PY + 1) * PX + pos + 1; edst[nexp + e] = 0 * edge_stride + e; }
-        }
-        if (hasN) nexp += segNS;
-        for (int e = tid; e < segNS; e += NTHREADS) {
-            const int t = e / tx, pos = e - t * tx;
-            if (hasS) { esrc[nexp + e] = (t * PY + ty) * PX + pos + 1; edst[nexp + e] = 1 * edge_stride + e; }
-        }
-        if (hasS) nexp += segNS;
-        for (int e = tid; e < segWE; e += NTHREADS) {
-            const int t = e / ty, pos = e - t * ty;
-            if (hasW) { esrc[nexp + e] = (t * PY + pos + 1) * PX + 1; edst[nexp + e] = 2 * edge_stride + e; }
-        }
-        if (hasW) nexp += segWE;
-        for (int e = tid; e < segWE; e += NTHREADS) {
-            const int t = e / ty, pos = e - t * ty;
-            if (hasE) { esrc[nexp + e] = (t * PY + pos + 1) * PX + tx; edst[nexp + e] = 3 * edge_stride + e; }
-        }
-        if (hasE) nexp += segWE;
     }
     // patch ownership: first tile row, number of owned rows, index of cell (t = 0, jy = 0) in rs
     const int ly0 = r0 * YPT;
@@ -140,7 +155,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
     auto fresh = [](int v) { asm volatile("" : "+r"(v)); return v; };
 
     double pj[CPT], sj[CPT];
-    __syncthreads();                                     // rs zeroed before the owners fill it
+    for (int i = tid; i < 2 * NT * (tx + ty); i += NTHREADS) shs[i] = 0.0;
 #pragma unroll
     for (int j = 0; j < CPT; j++) { pj[j] = 0.0; sj[j] = 0.0; if (!XG) xs[j * NTHREADS + tid] = 0.0; ws[j * NTHREADS + tid] = 0.0; }
 #pragma unroll
@@ -154,35 +169,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
             }
         }
     }
-    // export pass (all threads, after a __syncthreads that follows the writes of rs): the tile-edge values of
-    // generation gn are rounded to its parity in place (so the owner and the neighbour use the same value) and stored;
-    // a corner cell sits in two lists and is rounded twice to the same value
-    auto export_edges = [&](unsigned int gn) {
-        const long long par = (long long)(gn & 1u);
+    // export pass (after a __syncthreads that follows the writes of ws): the tile-edge values of w of iteration k are
+    // rounded to the tag in place (so the owner and the neighbour use the same value) and stored into parity buffer
+    // k & 1; a corner cell sits in two lists and is rounded twice to the same value
+    auto export_edges = [&](unsigned int k) {
+        const long long tag = (long long)((k >> 1) & 1u);
+        double *dst = my_edges + (size_t)(k & 1u) * ebuf;
+        if (etid >= 0) {
 #pragma unroll
-        for (int e = 0; e < kHaloPerThread; e++) {
-            const int h = tid + e * NTHREADS;
-            if (h < nexp) {
-                const int si = esrc[h];
-                const double v = __longlong_as_double((__double_as_longlong(rs[si]) & ~1ll) | par);
-                rs[si] = v;
-                st_relaxed_u64((unsigned long long *)(my_edges + edst[h]), (unsigned long long)__double_as_longlong(v));
+            for (int e = 0; e < kHaloPerThread; e++) {
+                const int h = etid + e * estride;
+                if (h < nhalo) {
+                    const int4 te = htab[h];
+                    const int si = te.z;
+                    const double v = __longlong_as_double((__double_as_longlong(ws[si]) & ~1ll) | tag);
+                    ws[si] = v;
+                    st_relaxed_u64((unsigned long long *)(dst + te.w), (unsigned long long)__double_as_longlong(v));
+                }
             }
         }
     };
-    __syncthreads();
-    export_edges(0u);
 
-    // x slot j += c * p_j  (slots [j0, j1)); XG: read-modify-write of the owned cell in global memory
+    // x slot j += c * p_j; XG: reduction into the owned cell in global memory (L2)
     double *const xg = a.x + ((size_t)(y0 + ly0)) * Nx + (x0 + lx);
     const size_t Pst = (size_t)Ny * Nx;
-    auto x_update = [&](int j0, int j1, double c) {
+    auto x_update = [&](double c) {
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
-            if (j < j0 || j >= j1) continue;
             if (XG) {
                 const int t = j / YPT, jy = j - t * YPT;
-                if (jy < nval) { double *px = xg + t * Pst + (size_t)jy * Nx; *px = *px + c * pj[j]; }
+                if (jy < nval) red_add_f64(xg + t * Pst + (size_t)jy * Nx, c * pj[j]);
             } else {
                 const int xi = j * NTHREADS + tid;
                 xs[xi] = xs[xi] + c * pj[j];
@@ -194,43 +210,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
     long long tmark = 0;
     const bool prof = g.prof != nullptr && tid == 0;
     long long *sprof = (long long *)(red + 72);           // shared-memory accumulators (thread 0 only)
-    if (tid == 0) { for (int k = 0; k < 6; k++) sprof[k] = 0; red[66] = 0.0; }
+    if (tid == 0) { for (int k = 0; k < 6; k++) sprof[k] = 0; red[66] = 0.0; red[67] = 0.0; }
     auto lap = [&](int k) { if (prof) { long long now = clock64(); sprof[k] += now - tmark; tmark = now; } };
 
     int it = 0, status = a.maxiter;
     double gam_stop = 0.0, rgam_prev = 0.0, d_prev = 0.0, alpha_prev = 0.0;
     bool pend = false;                                   // x += alpha_prev p not yet applied
+    __syncthreads();                                     // rs (interior and ring) complete
     if (prof) tmark = clock64();
     for (; it < a.maxiter; it++) {
-        // ---- import the neighbours' edge values of generation `it`: spin on every word until its parity is it & 1
-        {
-            const double *eg = g.edges;
-            const unsigned long long par = (unsigned long long)(it & 1);
-            double hv[kHaloPerThread];
-            const long long t0 = clock64();
-            bool ready;
-            do {
-                ready = true;
-#pragma unroll
-                for (int e = 0; e < kHaloPerThread; e++) {
-                    const int h = tid + e * NTHREADS;
-                    hv[e] = 0.0;
-                    if (h < nhalo) {
-                        const unsigned long long bits = ld_relaxed_u64((const unsigned long long *)(eg + hsrc[h]));
-                        ready = ready && (bits & 1ull) == par;
-                        hv[e] = __longlong_as_double((long long)bits);
-                    }
-                }
-                if (!ready && clock64() - t0 > kWatchdogCycles) { red[66] = 1.0; break; }     // a neighbour is stuck: abort below
-            } while (!ready);
-#pragma unroll
-            for (int e = 0; e < kHaloPerThread; e++) {
-                const int h = tid + e * NTHREADS;
-                if (h < nhalo) rs[hdst[h]] = hv[e];
-            }
-        }
-        __syncthreads();
-        lap(0);
         // ---- w = A r (csr_matvec order), partial r.r and r.w
         double acc[2] = {0.0, 0.0};
         if (nval > 0) {
@@ -274,24 +262,67 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
                 }
             }
         }
-        lap(1);
-        // ---- the one all-reduce; the x update of the previous iteration runs in its shadow
-        block_sum<2>(acc, red);
-        if (tid == 0) grid_arrive<2>(g.slots, gen, acc, red[66] != 0.0);    // an import watchdog of this CTA aborts the whole grid
-        if (cta == 0 && tid < 32) grid_root<2>(g.slots, gen, ncta, tid);
-        if (pend) {                                      // second half of x += alpha_prev p (first half: after the export)
-            x_update(CPT / 2, CPT, alpha_prev);
-            pend = false;
+        lap(0);
+        // ---- the one all-reduce; in its shadow: export of the edges of w, x update of the previous iteration,
+        //      import of the neighbours' edges of w (into registers)
+        {                                                // block total in warp 0 only (block_sum of common.cuh without the broadcast)
+            acc[0] = warp_sum(acc[0]); acc[1] = warp_sum(acc[1]);
+            if ((tid & 31) == 0) { red[tid >> 5] = acc[0]; red[32 + (tid >> 5)] = acc[1]; }
+            __syncthreads();                             // also orders the writes of ws before the export
+            if (tid < 32) {
+                acc[0] = warp_sum(tid < NTHREADS / 32 ? red[tid] : 0.0);
+                acc[1] = warp_sum(tid < NTHREADS / 32 ? red[32 + tid] : 0.0);
+                if (tid == 0) grid_arrive<2>(g.slots, gen, acc);
+                if (cta == 0) grid_root<2>(g.slots, gen, ncta, tid);
+            }
         }
+        export_edges((unsigned int)it);
+        if (pend) { x_update(alpha_prev); pend = false; }
+        double hv[kHaloPerThread] = {0.0, 0.0, 0.0, 0.0};
+        auto import_edges = [&]() {
+            if (etid >= 0) {
+                const double *eg = g.edges + (size_t)(it & 1) * ebuf;
+                const unsigned long long tag = (unsigned long long)((it >> 1) & 1);
+                const long long t0 = clock64();
+                int rounds = 0;
+                bool ready;
+                do {
+                    ready = true;
+#pragma unroll
+                    for (int e = 0; e < kHaloPerThread; e++) {
+                        const int h = etid + e * estride;
+                        hv[e] = 0.0;
+                        if (h < nhalo) {
+                            const unsigned long long bits = ld_relaxed_u64((const unsigned long long *)(eg + htab[h].x));
+                            ready = ready && (bits & 1ull) == tag;
+                            hv[e] = __longlong_as_double((long long)bits);
+                        }
+                    }
+                    rounds++;
+                    if (!ready && clock64() - t0 > kWatchdogCycles) { red[66] = 1.0; break; }     // a neighbour is stuck: abort below
+                } while (!ready);
+                if (g.prof != nullptr && tid == 32) { sprof[4] += rounds; sprof[5] += clock64() - t0; }
+            }
+        };
+        import_edges();
+        lap(1);
         if (tid == 0) {
-            if (!grid_wait<2>(g.slots, gen, red + 64)) red[66] = 1.0;
+            if (!grid_wait<2>(g.slots, gen, red + 64)) red[67] = 1.0;
         }
         __syncthreads();
         gen++;
         const double gam = red[64], del = red[65];
-        abort = red[66] != 0.0;
+        abort = red[67] != 0.0;
         lap(2);
         if (abort) break;
+        if (red[66] != 0.0) {                            // import watchdog of this CTA: one more round that tells every CTA
+            __syncthreads();
+            if (tid == 0) grid_arrive<2>(g.slots, gen, acc, true);
+            if (cta == 0 && tid < 32) grid_root<2>(g.slots, gen, ncta, tid);
+            if (tid == 0) grid_wait<2>(g.slots, gen, red + 64);
+            abort = true;
+            break;
+        }
         if (it == 0) {
             if (gam == 0.0) { status = 0; break; }       // scipy: "if bnrm2 == 0: return b, 0"
             // scipy stops when sqrt(gamma) < atol, atol = rtol sqrt(gamma_0).  sqrt is monotone and correctly rounded,
@@ -310,7 +341,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
         const double beta = gam * rgam_prev;
         const double dk = del - (beta * beta) * d_prev;
         const double alpha = gam / dk;
-        // ---- p = r + beta p, s = w + beta s, r -= alpha s; tile-edge values exported as generation it+1
+        // ---- p = r + beta p, s = w + beta s, r -= alpha s on the owned cells ...
 #pragma unroll
         for (int jy = 0; jy < YPT; jy++) {
             if (jy < nval) {
@@ -325,12 +356,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
                 }
             }
         }
+        // ... and, with the same arithmetic, s and r on the halo ring (the neighbours' edge cells)
+        if (etid >= 0) {
+#pragma unroll
+            for (int e = 0; e < kHaloPerThread; e++) {
+                const int h = etid + e * estride;
+                if (h < nhalo) {
+                    const int di = htab[h].y;
+                    const double sv = shs[h] * beta + hv[e];
+                    shs[h] = sv;
+                    rs[di] = rs[di] - alpha * sv;
+                }
+            }
+        }
         __syncthreads();
-        export_edges((unsigned int)it + 1u);
         lap(3);
-        // first half of x += alpha p while the edge values travel
-        x_update(0, CPT / 2, alpha);
-        lap(4);
         pend = true; alpha_prev = alpha; d_prev = dk;
         rgam_prev = 1.0 / gam;                           // not needed before the next all-reduce has completed
     }
@@ -343,9 +383,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
             for (int t = 0; t < NT; t++) {
                 const int j = t * YPT + jy;
                 double *px = a.x + ((size_t)t * Ny + (y0 + ly0 + jy)) * Nx + (x0 + lx);
-                double xv = XG ? *px : xs[j * NTHREADS + tid];
-                if (pend && j >= CPT / 2) xv = xv + alpha_prev * pj[j];
-                if (!XG || (pend && j >= CPT / 2)) *px = xv;
+                if (XG) {
+                    if (pend) red_add_f64(px, alpha_prev * pj[j]);
+                } else {
+                    double xv = xs[j * NTHREADS + tid];
+                    if (pend) xv = xv + alpha_prev * pj[j];
+                    *px = xv;
+                }
             }
         }
     }
@@ -377,9 +421,8 @@ struct Plan { bool ok = false; int shape = 0, gy = 0, gx = 0, maxlen = 0, ncta =
 
 // Tile grid: gy*gx <= #SMs, every tile fits the 4 x 4 patches of 512 threads, the halo tables and shared memory.
 // Every grid that fits costs an active thread the same 16 cell slots; what differs is measured (tools/sweep_grid.py,
-// 388x584x4, SWEEP_VARIANT=2: 5.87 us per iteration for 12x12, 5.96 for 8x18, 6.2-6.6 for the rest): tiles whose
-// width is a multiple of 16 (+1) keep a half-warp inside one row group, i.e. free of shared-memory bank conflicts;
-// then short halos and few idle SMs; then wide rows.
+// 388x584x4, SWEEP_VARIANT=2: 5.87 us per iteration for 12x12, 5.96 for 8x18, 6.2-6.6 for the rest): short halos and few idle SMs first, then wide rows.  (Padding the rows of r so that a half-warp running off a thread row
+// continues on the following banks -- conflict free for any tile width -- was measured: no gain, 5.00 against 4.97 us.)
 Plan make_plan(OnchipScratch &d, int device, int Nt, int Ny, int Nx)
 {
     Plan best;
@@ -404,12 +447,11 @@ Plan make_plan(OnchipScratch &d, int device, int Nt, int Ny, int Nx)
             bool fits = true;
             for (int txx = tx_min; txx <= tx; txx++) if (ty > kYPT * (kThreads / txx)) fits = false;
             if (!fits) continue;
-            if (2LL * kNT * (tx + ty) > (long long)kHaloPerThread * kThreads) continue;
-            const size_t smem = ((((size_t)kNT * (ty + 2) * (tx + 2) + 1) & ~size_t(1)) + (size_t)xslots * kNT * kYPT * kThreads + 80 + 4) * 8
-                              + (size_t)8 * kNT * (tx + ty) * sizeof(int);
+            if (2LL * kNT * (tx + ty) > (long long)kHaloPerThread * (kThreads - 32)) continue;
+            const size_t smem = ((((size_t)kNT * (ty + 2) * (tx + 2) + 1) & ~size_t(1)) + (size_t)xslots * kNT * kYPT * kThreads + 80 + 4
+                                 + (size_t)2 * kNT * (tx + ty)) * 8 + (size_t)8 * kNT * (tx + ty) * sizeof(int);
             if (smem > d.smem_optin) continue;
-            const int straddle = (tx % 16) > 1 ? 1 : 0;
-            const long long key = ((straddle * 100000LL + 2LL * kNT * (tx + ty) + 8LL * (d.num_sms - gy * gx)) * 1000) + (999 - tx);
+            const long long key = ((2LL * kNT * (tx + ty) + 8LL * (d.num_sms - gy * gx)) * 1000) + (999 - tx);
             if (best_key < 0 || key < best_key) {
                 best_key = key; best.ok = true; best.gy = gy; best.gx = gx; best.ncta = gy * gx;
                 best.maxlen = tx > ty ? tx : ty; best.smem = smem;
@@ -435,7 +477,7 @@ int launch_cg_fused(cudaStream_t st, const CgArgs &a, int device, OnchipScratch 
 {
     Plan p = make_plan(d, device, a.Nt, a.Ny, a.Nx);
     if (!p.ok) { set_error("grid %dx%dx%d does not fit the single-reduction on-chip CG variant", a.Nt, a.Ny, a.Nx); return FOTO_ERR_ARG; }
-    const size_t need = (size_t)p.ncta * 4 * a.Nt * p.maxlen * sizeof(double);
+    const size_t need = (size_t)2 * p.ncta * 4 * a.Nt * p.maxlen * sizeof(double);     // two parity buffers
     if (d.fused_edges_bytes < need) {
         if (d.fused_edges) CUDA_TRY(cudaFree(d.fused_edges));
         CUDA_TRY(cudaMalloc((void **)&d.fused_edges, need));
@@ -451,7 +493,7 @@ int launch_cg_fused(cudaStream_t st, const CgArgs &a, int device, OnchipScratch 
         d.fused_attr_set = true;
     }
     const int nedge = (int)(need / sizeof(double));
-    // all-reduce slots and edge words <- odd parity ("generation 0 not yet written")
+    // all-reduce slots and edge words <- tag 1 ("generations 0 and 1 not yet written")
     k_fill2_u64<<<((nedge > kSlotWords ? nedge : kSlotWords) + 255) / 256, 256, 0, st>>>(d.fused_slots, kSlotWords, kSlotInit, (unsigned long long *)d.fused_edges, nedge, ~0ull);
     Geom g;
     g.gy = p.gy; g.gx = p.gx; g.maxlen = p.maxlen; g.edges = d.fused_edges; g.slots = d.fused_slots; g.prof = d.prof;

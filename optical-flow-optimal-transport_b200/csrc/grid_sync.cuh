@@ -3,8 +3,8 @@
 // Two-hop root gather through L2: thread 0 of every CTA stores its partial sums, warp 0 of CTA 0 sums the partials
 // in a fixed order and stores the totals, thread 0 of every CTA polls the totals.  Every CTA gets bit-identical
 // totals.  2 260-2 750 cycles for 144-148 CTAs and two values (tools/ubench_allreduce2.cu, variant A); one-hop
-// all-gathers, thread-block clusters with DSMEM pre-reduction and integer-atomic accumulation were measured slower or
-// equal (profiles/r2_allreduce_variants.md): the cost is two L2 traversals, partly across the two dies.
+// all-gathers, thread-block clusters with DSMEM pre-reduction, integer-atomic accumulation and several staggered polls
+// in flight per waiter were measured slower or equal (profiles/r2_allreduce_variants.md): the cost is two L2 traversals, partly across the two dies.
 //
 // Memory model.  Every communicated word validates itself: bit 0 of the mantissa carries the parity of the
 // generation the word belongs to (a one-ulp rounding of a partial sum / total, the same value for every reader), and

@@ -35,7 +35,7 @@ for variant, cfg in ((0, None), (2, None)):
         c = ctx.onchip_prof(False)
         c = c[c[:, 6] > 0].astype(float)
         it = c[:, 6:7]
-        names = ["halo import (spin)", "stencil", "all-reduce (+x/2)", "p,s,r update+export", "x/2 (hop)", "-"]
+        names = ["stencil", "reduce+export+x+import", "all-reduce wait", "p,s,r + ring update", "import rounds (thread 32)", "import cycles (thread 32)"]
         per = c[:, :6] / it
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         np.savetxt(os.path.join(ROOT, "gpurun_out", f"phase_cycles_variant{variant}_cfg{cfg}.csv"), per, fmt="%.0f", delimiter=",")
@@ -43,9 +43,9 @@ for variant, cfg in ((0, None), (2, None)):
         for k, n in enumerate(names):
             col = per[:, k]
             print(f"   {n:20s} {col[0]:9.0f} {col.min():8.0f} {np.median(col):8.0f} {col.max():8.0f} {int(col.argmax()):6d}")
-        tot = per.sum(axis=1)
+        tot = per[:, :4].sum(axis=1)
         print(f"   {'total':20s} {tot[0]:9.0f} {tot.min():8.0f} {np.median(tot):8.0f} {tot.max():8.0f}")
-        comp = per[:, [0, 1, 3]].sum(axis=1)
+        comp = per[:, [0, 3]].sum(axis=1)
         print(f"   compute (no barriers, no x): min {comp.min():.0f} median {np.median(comp):.0f} max {comp.max():.0f} at CTA {int(comp.argmax())}")
     if variant >= 1:
         print("   max |u_onchip - u_stream| / max|u| =", float(np.max(np.abs(res[0] - res[variant])) / np.max(np.abs(res[0]))))
