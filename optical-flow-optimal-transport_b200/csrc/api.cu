@@ -280,26 +280,37 @@ static int fetch_result(foto_ctx *c)
 static int ensure_dct_tables(foto_ctx *c, const Dims &d)
 {
     DctTables &t = c->dct;
-    if (t.base && t.Nt == d.Nt && t.Ny == d.Ny && t.Nx == d.Nx) return FOTO_OK;
+    const bool split = d.Nx % 4 == 0 && d.Ny % 4 == 0 && getenv("FOTO_DCT_DENSE") == nullptr;     // even / odd folded x and y transforms
+    if (t.base && t.Nt == d.Nt && t.Ny == d.Ny && t.Nx == d.Nx && t.split == split) return FOTO_OK;
     if (t.base) { CUDA_TRY(cudaFree(t.base)); t = DctTables(); }
     const int n[3] = {d.Nx, d.Ny, d.Nt};
-    size_t total = 0;
-    for (int a = 0; a < 3; a++) total += 2 * (size_t)n[a] * n[a] + n[a];
-    std::vector<double> host; host.reserve(total);
+    std::vector<double> host;
     std::vector<size_t> off;
+    auto push = [&](const std::vector<double> &v) {
+        if (host.size() & 1) host.push_back(0.0);        // every table starts on a 16-byte boundary
+        off.push_back(host.size()); host.insert(host.end(), v.begin(), v.end());
+    };
     for (int a = 0; a < 3; a++) {
         std::vector<double> C, Ct, lam;
         dct_host_tables(n[a], C, Ct, lam);
-        off.push_back(host.size()); host.insert(host.end(), C.begin(), C.end());
-        off.push_back(host.size()); host.insert(host.end(), Ct.begin(), Ct.end());
-        off.push_back(host.size()); host.insert(host.end(), lam.begin(), lam.end());
+        push(C); push(Ct); push(lam);
+        if (split && a < 2) {
+            std::vector<double> E, ET, lam_p;
+            dct_host_folded(n[a], C, lam, E, ET, lam_p);
+            push(E); push(ET); push(lam_p);
+        }
     }
+    const size_t total = host.size();
     CUDA_TRY(cudaMalloc((void **)&t.base, total * sizeof(double)));
     CUDA_TRY(cudaMemcpyAsync(t.base, host.data(), total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));          // host vector goes out of scope
-    t.Cx = t.base + off[0]; t.CxT = t.base + off[1]; t.lam_x = t.base + off[2];
-    t.Cy = t.base + off[3]; t.CyT = t.base + off[4]; t.lam_y = t.base + off[5];
-    t.Ct = t.base + off[6]; t.CtT = t.base + off[7]; t.lam_t = t.base + off[8];
+    int k = 0;
+    t.Cx = t.base + off[k++]; t.CxT = t.base + off[k++]; t.lam_x = t.base + off[k++];
+    if (split) { t.Ex = t.base + off[k++]; t.ExT = t.base + off[k++]; t.lam_xp = t.base + off[k++]; }
+    t.Cy = t.base + off[k++]; t.CyT = t.base + off[k++]; t.lam_y = t.base + off[k++];
+    if (split) { t.Ey = t.base + off[k++]; t.EyT = t.base + off[k++]; t.lam_yp = t.base + off[k++]; }
+    t.Ct = t.base + off[k++]; t.CtT = t.base + off[k++]; t.lam_t = t.base + off[k++];
+    t.split = split;
     t.Nt = d.Nt; t.Ny = d.Ny; t.Nx = d.Nx;
     return FOTO_OK;
 }
@@ -316,7 +327,7 @@ static int run_cg(foto_ctx *c, const Dims &d, const double *F, double *phi, doub
         // report "0 iterations, converged" through the same result block the CG kernels write
         CUDA_TRY(cudaMemsetAsync(&c->d_res->cg_iters, 0, 2 * sizeof(int), c->stream));
         c->stats.cg_variant = 2;
-        c->stats.launches += 5; c->stats.cg_launches++;
+        c->stats.launches += c->dct.split ? 9 : 5; c->stats.cg_launches++;
         return FOTO_OK;
     }
     CgArgs a;
@@ -1084,7 +1095,7 @@ extern "C" int foto_dct_xy_dev(foto_ctx *c, const double *in, double *out, doubl
     FOTO_TRY(ctx_bind(c));
     FOTO_TRY(ensure_dct_tables(c, d));
     FOTO_TRY(launch_dct_xy(c->stream, c->dct, nplanes, Ny, Nx, in, out, tmp, inverse));
-    c->stats.launches += 2;
+    c->stats.launches += c->dct.split ? 4 : 2;
     return FOTO_OK;
 }
 

@@ -11,7 +11,8 @@
 // with its inner CG run to rtol 1e-13), never the default.
 //
 // Transforms are batched dense fp64 GEMMs (584 = 8*73 and 388 = 4*97 are FFT-hostile; 3.5 GFLOP
-// per solve at 388x584x4) on the fp64 tensor-core MMA (m8n8k4, SASS DMMA): see k_dgemm_nn.
+// per solve at 388x584x4) on the fp64 tensor-core MMA (m8n8k4, SASS DMMA): see k_dgemm_nn.  When Nx and Ny are
+// multiples of 4 the even / odd symmetry of the DCT matrix halves the flops (k_fold / k_unfold, launch_dct_xy).
 #include <cmath>
 
 #include "foto_kernels.cuh"
@@ -20,16 +21,21 @@ namespace foto {
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, GT = 128, STAGES = 2;   // 4 warps, each a 32x32 output tile
+constexpr int BK = 16;
 constexpr int APITCH = BK + 4;       // = 4 (mod 16): the 8x4 A fragment of a half-warp hits 16 distinct bank pairs
-constexpr int BPITCH = BN + 4;       // = 4 (mod 16): same for the 4x8 B fragment
 
-// 8-byte asynchronous global -> shared copy (LDGSTS), zero-filled when !valid
+// 8- / 16-byte asynchronous global -> shared copy (LDGSTS), zero-filled when !valid
 __device__ __forceinline__ void cp_async8(double *dst, const double *src, bool valid)
 {
     const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst);
     const int bytes = valid ? 8 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16(double *dst, const double *src, bool valid)
+{
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst);
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
 
 // D(8x8) += A(8x4, row) * B(4x8, col), fp64 tensor-core MMA (SASS: DMMA)
@@ -39,23 +45,35 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// C[b] = A[b] * B[b], row-major, A: M x K (lda), B: K x N (ldb), C: M x N (ldc); batch strides in doubles.
+struct GemmBatch {                    // two-level batch: blockIdx.z = z1 * nb0 + z0, offsets in doubles
+    int nb0;
+    long long a0, a1, b0, b1, c0, c1;
+};
+
+// C[z] = A[z] * B[z], row-major, A: M x K (lda), B: K x N (ldb), C: M x N (ldc).
 // A register-tiled CUDA-core version of this kernel (4x4 outputs per thread) ran at 17 % of the fp64
 // peak with the shared-memory pipe 50-58 % busy (ncu): operand delivery, not the fp64 pipe, was the
 // limit.  The m8n8k4 fp64 MMA shares each operand across the warp inside the tensor-core datapath:
 // a warp tile of 32x32 needs 8 shared-memory doubles per thread for 128 FMAs per thread (the 4x4
-// CUDA-core tile: 8 doubles for 16 FMAs).  Operand tiles travel global -> shared with cp.async, one
-// k-tile ahead of the MMAs.
-__global__ void __launch_bounds__(GT) k_dgemm_nn(int M, int N, int K, const double *__restrict__ A, int lda,
-                                                  long long strideA, const double *__restrict__ B, int ldb,
-                                                  long long strideB, double *__restrict__ C, int ldc, long long strideC)
+// CUDA-core tile: 8 doubles for 16 FMAs).  Operand tiles travel global -> shared with cp.async through a
+// STAGES-deep ring; VEC: 16-byte copies (all leading dimensions, K, N and the base offsets even).
+// Block tile BM x BN, (BM / 32) x (BN / 32) warps of 32 x 32 each.
+template <int BM, int BN, int STAGES, bool VEC>
+__global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32) k_dgemm_nn(int M, int N, int K, const double *__restrict__ A, int lda,
+                                                                        const double *__restrict__ B, int ldb, double *__restrict__ C,
+                                                                        int ldc, GemmBatch gb)
 {
-    __shared__ __align__(16) double As[STAGES][BM][APITCH];   // As[m][k]
-    __shared__ __align__(16) double Bs[STAGES][BK][BPITCH];   // Bs[k][n]
-    A += (size_t)blockIdx.z * strideA; B += (size_t)blockIdx.z * strideB; C += (size_t)blockIdx.z * strideC;
+    constexpr int GT = (BM / 32) * (BN / 32) * 32, BPITCH = BN + 4;       // = 4 (mod 16): same for the 4x8 B fragment
+    extern __shared__ __align__(16) double dsm[];
+    double (*As)[BM][APITCH] = reinterpret_cast<double (*)[BM][APITCH]>(dsm);                          // As[stage][m][k]
+    double (*Bs)[BK][BPITCH] = reinterpret_cast<double (*)[BK][BPITCH]>(dsm + STAGES * BM * APITCH);   // Bs[stage][k][n]
+    {
+        const int z0 = blockIdx.z % gb.nb0, z1 = blockIdx.z / gb.nb0;
+        A += z0 * gb.a0 + z1 * gb.a1; B += z0 * gb.b0 + z1 * gb.b1; C += z0 * gb.c0 + z1 * gb.c1;
+    }
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;              // warp tile origin inside the block tile
+    const int wm = (warp / (BN / 32)) * 32, wn = (warp % (BN / 32)) * 32;  // warp tile origin inside the block tile
     const int fr = lane >> 2, fc = lane & 3;                            // fragment row / column of this lane
     double acc[4][4][2];
 #pragma unroll
@@ -63,31 +81,52 @@ __global__ void __launch_bounds__(GT) k_dgemm_nn(int M, int N, int K, const doub
 #pragma unroll
         for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-    // A tile 64 x 16: 8 passes of (row = pass*8 + tid/16, k = tid%16); B tile 16 x 64: 8 passes of (row = pass*2 + tid/64, col = tid%64)
     auto prefetch = [&](int stage, int k0) {
+        if (VEC) {
+            // A tile BM x 16: 8 two-double chunks per row; B tile 16 x BN: BN / 2 chunks per row
 #pragma unroll
-        for (int ps = 0; ps < 8; ps++) {
-            const int r = ps * 8 + (tid >> 4), c = tid & 15;
-            const int gm = m0 + r, gk = k0 + c;
-            const bool ok = gm < M && gk < K;
-            cp_async8(&As[stage][r][c], ok ? A + (size_t)gm * lda + gk : A, ok);
-        }
+            for (int ps = 0; ps < BM * 8 / GT; ps++) {
+                const int idx = ps * GT + tid, r = idx >> 3, c = (idx & 7) * 2;
+                const int gm = m0 + r, gk = k0 + c;
+                const bool ok = gm < M && gk < K;
+                cp_async16(&As[stage][r][c], ok ? A + (size_t)gm * lda + gk : A, ok);
+            }
 #pragma unroll
-        for (int ps = 0; ps < 8; ps++) {
-            const int r = ps * 2 + (tid >> 6), c = tid & 63;
-            const int gk = k0 + r, gn = n0 + c;
-            const bool ok = gk < K && gn < N;
-            cp_async8(&Bs[stage][r][c], ok ? B + (size_t)gk * ldb + gn : B, ok);
+            for (int ps = 0; ps < BK * (BN / 2) / GT; ps++) {
+                const int idx = ps * GT + tid, r = idx / (BN / 2), c = (idx % (BN / 2)) * 2;
+                const int gk = k0 + r, gn = n0 + c;
+                const bool ok = gk < K && gn < N;
+                cp_async16(&Bs[stage][r][c], ok ? B + (size_t)gk * ldb + gn : B, ok);
+            }
+        } else {
+#pragma unroll
+            for (int ps = 0; ps < BM * BK / GT; ps++) {
+                const int idx = ps * GT + tid, r = idx / BK, c = idx % BK;
+                const int gm = m0 + r, gk = k0 + c;
+                const bool ok = gm < M && gk < K;
+                cp_async8(&As[stage][r][c], ok ? A + (size_t)gm * lda + gk : A, ok);
+            }
+#pragma unroll
+            for (int ps = 0; ps < BK * BN / GT; ps++) {
+                const int idx = ps * GT + tid, r = idx / BN, c = idx % BN;
+                const int gk = k0 + r, gn = n0 + c;
+                const bool ok = gk < K && gn < N;
+                cp_async8(&Bs[stage][r][c], ok ? B + (size_t)gk * ldb + gn : B, ok);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     const int nk = (K + BK - 1) / BK;
-    prefetch(0, 0);
+#pragma unroll
+    for (int s0 = 0; s0 < STAGES - 1; s0++) {
+        if (s0 < nk) prefetch(s0, s0 * BK); else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     for (int kt = 0; kt < nk; kt++) {
-        const int st = kt & 1;
-        if (kt + 1 < nk) prefetch(st ^ 1, (kt + 1) * BK); else asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");     // k-tile kt has landed
-        __syncthreads();
+        const int st = kt % STAGES;
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");     // k-tile kt has landed
+        __syncthreads();                                                          // ... and stage (kt-1) % STAGES is free
+        if (kt + STAGES - 1 < nk) prefetch((kt + STAGES - 1) % STAGES, (kt + STAGES - 1) * BK);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll
         for (int k4 = 0; k4 < BK; k4 += 4) {
             double a[4], b[4];
@@ -100,7 +139,6 @@ __global__ void __launch_bounds__(GT) k_dgemm_nn(int M, int N, int K, const doub
 #pragma unroll
                 for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
-        __syncthreads();                                          // stage st may be overwritten by the next prefetch
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -112,6 +150,34 @@ __global__ void __launch_bounds__(GT) k_dgemm_nn(int M, int N, int K, const doub
             if (gn < N) C[(size_t)gm * ldc + gn] = acc[i][j][0];
             if (gn + 1 < N) C[(size_t)gm * ldc + gn + 1] = acc[i][j][1];
         }
+    }
+}
+
+// Even / odd folding of a DCT along the middle axis of an [outer][n][inner] array (n even, h = n / 2).  The DCT-II
+// matrix satisfies C[k][n-1-i] = (-1)^k C[k][i], so
+//   forward:  X[2j]   = sum_{i<h} C[2j][i]   (x[i] + x[n-1-i]),   X[2j+1] = sum_{i<h} C[2j+1][i] (x[i] - x[n-1-i])
+//   inverse:  x[i] = E[i] + O[i],  x[n-1-i] = E[i] - O[i],  E = sum_j C[2j][i] X[2j],  O = sum_j C[2j+1][i] X[2j+1]
+// i.e. two h x h transforms instead of one n x n: half the flops.  fold: out[b][outer][h][inner] (b = 0 sums, 1 differences)
+__global__ void __launch_bounds__(256) k_fold(size_t total, int n, int inner, const double *__restrict__ in, double *__restrict__ out, size_t bstride)
+{
+    const int h = n >> 1;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = k % inner, oh = k / inner, o = oh / h;
+        const int j = (int)(oh % h);
+        const double a = in[(o * n + j) * inner + i], c = in[(o * n + (n - 1 - j)) * inner + i];
+        out[k] = a + c;
+        out[bstride + k] = a - c;
+    }
+}
+__global__ void __launch_bounds__(256) k_unfold(size_t total, int n, int inner, const double *__restrict__ in, size_t bstride, double *__restrict__ out)
+{
+    const int h = n >> 1;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = k % inner, oh = k / inner, o = oh / h;
+        const int j = (int)(oh % h);
+        const double e = in[k], d = in[bstride + k];
+        out[(o * n + j) * inner + i] = e + d;
+        out[(o * n + (n - 1 - j)) * inner + i] = e - d;
     }
 }
 
@@ -175,18 +241,65 @@ void dct_host_tables(int n, std::vector<double> &C, std::vector<double> &Ct, std
     }
 }
 
-static void gemm(cudaStream_t st, int M, int N, int K, const double *A, int lda, long long sA, const double *B, int ldb,
-                 long long sB, double *C, int ldc, long long sC, int batch)
+// Folded tables of one axis (n even): E[b][j][i] = C[2j+b][i], i < n/2; ET[b][i][j] = E[b][j][i]; lam_p = (lam[0], lam[2], ...,
+// lam[1], lam[3], ...)
+void dct_host_folded(int n, const std::vector<double> &C, const std::vector<double> &lam, std::vector<double> &E,
+                     std::vector<double> &ET, std::vector<double> &lam_p)
 {
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch);
-    k_dgemm_nn<<<grid, GT, 0, st>>>(M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC);
+    const int h = n / 2;
+    E.assign((size_t)2 * h * h, 0.0); ET.assign((size_t)2 * h * h, 0.0); lam_p.assign(n, 0.0);
+    for (int b = 0; b < 2; b++)
+        for (int j = 0; j < h; j++) {
+            lam_p[b * h + j] = lam[2 * j + b];
+            for (int i = 0; i < h; i++) {
+                const double c = C[(size_t)(2 * j + b) * n + i];
+                E[((size_t)b * h + j) * h + i] = c;
+                ET[((size_t)b * h + i) * h + j] = c;
+            }
+        }
 }
+
+template <int BM, int BN, int STAGES>
+struct DGemm {
+    static constexpr int smem = STAGES * (BM * APITCH + BK * (BN + 4)) * (int)sizeof(double);
+    static constexpr int threads = (BM / 32) * (BN / 32) * 32;
+    static int launch(cudaStream_t st, bool vec, int M, int N, int K, const double *A, int lda, const double *B, int ldb, double *C,
+                      int ldc, const GemmBatch &gb, int batch)
+    {
+        static bool prepared[64] = {};
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        if (dev < 64 && !prepared[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(k_dgemm_nn<BM, BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CUDA_TRY(cudaFuncSetAttribute(k_dgemm_nn<BM, BN, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            prepared[dev] = true;
+        }
+        dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch);
+        if (vec) k_dgemm_nn<BM, BN, STAGES, true><<<grid, threads, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, gb);
+        else k_dgemm_nn<BM, BN, STAGES, false><<<grid, threads, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, gb);
+        return FOTO_OK;
+    }
+};
+// 64 x 64 tiles, 4 warps, 3 stages, 37 KB: 31 TFLOP/s = 0.84 of the measured DMMA peak at 1080x1920x16.  128 x 128 tiles with 16
+// warps (a quarter of the L2 -> shared traffic per flop) were measured slower (28 TFLOP/s; half the speed on one Middlebury pair).
+using DGemm64 = DGemm<64, 64, 3>;
+
+static bool aligned16(const void *p) { return ((size_t)p & 15) == 0; }
+
+static int gemm(cudaStream_t st, int M, int N, int K, const double *A, int lda, const double *B, int ldb, double *C, int ldc,
+                const GemmBatch &gb, int batch)
+{
+    const bool even = !((lda | ldb | K | N) & 1) && !((gb.a0 | gb.a1 | gb.b0 | gb.b1) & 1) && aligned16(A) && aligned16(B);
+    return DGemm64::launch(st, even, M, N, K, A, lda, B, ldb, C, ldc, gb, batch);
+}
+
+static int fold_blocks(size_t total) { const size_t b = (total + 255) / 256; return (int)(b < 148 * 16 ? b : 148 * 16); }
 
 static int t_solve(cudaStream_t st, const DctTables &tb, int Nt, int Ny, int Nx, const double *lam_y, double r, double eps,
                    const double *in, double *out)
 {
     const int blocks = (int)(((long long)Ny * Nx + 255) / 256);
-#define FOTO_T_SOLVE(M) k_t_solve<M><<<blocks, 256, 0, st>>>(Nt, Ny, Nx, r, eps, tb.Ct, tb.lam_t, lam_y, tb.lam_x, in, out)
+#define FOTO_T_SOLVE(M) k_t_solve<M><<<blocks, 256, 0, st>>>(Nt, Ny, Nx, r, eps, tb.Ct, tb.lam_t, lam_y, tb.split ? tb.lam_xp : tb.lam_x, in, out)
     if (Nt <= 4) FOTO_T_SOLVE(4);
     else if (Nt <= 8) FOTO_T_SOLVE(8);
     else if (Nt <= 16) FOTO_T_SOLVE(16);
@@ -197,17 +310,45 @@ static int t_solve(cudaStream_t st, const DctTables &tb, int Nt, int Ny, int Nx,
     return FOTO_OK;
 }
 
-// x and y transforms of `nplanes` planes (forward: DCT-II, inverse: DCT-III); tmp: nplanes*Ny*Nx doubles
+// x and y transforms of `nplanes` planes (forward: DCT-II, inverse: DCT-III); tmp: nplanes*Ny*Nx doubles, in != out != tmp.
+// tb.split (Nx and Ny multiples of 4): even / odd folded transforms, half the flops; the spectrum then lives in the
+// permuted order "even frequencies, then odd frequencies" along x and y (tb.lam_xp / lam_yp are permuted alike; nothing
+// but the pointwise t solve ever looks at the spectrum).
 int launch_dct_xy(cudaStream_t st, const DctTables &tb, int nplanes, int Ny, int Nx, const double *in, double *out,
                   double *tmp, int inverse)
 {
     const long long P = (long long)Ny * Nx;
+    const GemmBatch one = {1, 0, 0, 0, 0, 0, 0};
+    if (!tb.split) {
+        if (!inverse) {
+            FOTO_TRY(gemm(st, nplanes * Ny, Nx, Nx, in, Nx, tb.CxT, Nx, tmp, Nx, one, 1));                     // rows * Cx^T
+            FOTO_TRY(gemm(st, Ny, Nx, Ny, tb.Cy, Ny, tmp, Nx, out, Nx, GemmBatch{1, 0, 0, 0, P, 0, P}, nplanes));   // Cy * plane
+        } else {
+            FOTO_TRY(gemm(st, Ny, Nx, Ny, tb.CyT, Ny, in, Nx, tmp, Nx, GemmBatch{1, 0, 0, 0, P, 0, P}, nplanes));
+            FOTO_TRY(gemm(st, nplanes * Ny, Nx, Nx, tmp, Nx, tb.Cx, Nx, out, Nx, one, 1));
+        }
+        CUDA_TRY(cudaGetLastError());
+        return FOTO_OK;
+    }
+    const int hx = Nx / 2, hy = Ny / 2, R = nplanes * Ny;
+    const size_t half = (size_t)nplanes * P / 2;          // elements of one folded half-volume
+    const long long hyNx = (long long)hy * Nx;
     if (!inverse) {
-        gemm(st, nplanes * Ny, Nx, Nx, in, Nx, 0, tb.CxT, Nx, 0, tmp, Nx, 0, 1);       // rows * Cx^T
-        gemm(st, Ny, Nx, Ny, tb.Cy, Ny, 0, tmp, Nx, P, out, Nx, P, nplanes);            // Cy * plane
+        // x: fold -> tmp = [b][R][hx];  out[r][b hx + j] = sum_n tmp[b][r][n] Cx[2j+b][n]
+        k_fold<<<fold_blocks(half), 256, 0, st>>>(half, Nx, 1, in, tmp, half);
+        FOTO_TRY(gemm(st, R, hx, hx, tmp, hx, tb.ExT, hx, out, Nx, GemmBatch{2, (long long)R * hx, 0, (long long)hx * hx, 0, hx, 0}, 2));
+        // y: fold -> tmp = [b][plane][hy][Nx];  out[plane][b hy + j][x] = sum_y Cy[2j+b][y] tmp[b][plane][y][x]
+        k_fold<<<fold_blocks(half), 256, 0, st>>>(half, Ny, Nx, out, tmp, half);
+        FOTO_TRY(gemm(st, hy, Nx, hy, tb.Ey, hy, tmp, Nx, out, Nx,
+                      GemmBatch{2, (long long)hy * hy, 0, (long long)nplanes * hyNx, hyNx, hyNx, P}, 2 * nplanes));
     } else {
-        gemm(st, Ny, Nx, Ny, tb.CyT, Ny, 0, in, Nx, P, tmp, Nx, P, nplanes);
-        gemm(st, nplanes * Ny, Nx, Nx, tmp, Nx, 0, tb.Cx, Nx, 0, out, Nx, 0, 1);
+        // y: tmp[b][plane][y][x] = sum_j Cy[2j+b][y] in[plane][b hy + j][x];  unfold -> out
+        FOTO_TRY(gemm(st, hy, Nx, hy, tb.EyT, hy, in, Nx, tmp, Nx,
+                      GemmBatch{2, (long long)hy * hy, 0, hyNx, P, (long long)nplanes * hyNx, hyNx}, 2 * nplanes));
+        k_unfold<<<fold_blocks(half), 256, 0, st>>>(half, Ny, Nx, tmp, half, out);
+        // x: tmp[b][r][n] = sum_j out[r][b hx + j] Cx[2j+b][n];  unfold -> out
+        FOTO_TRY(gemm(st, R, hx, hx, out, Nx, tb.Ex, hx, tmp, hx, GemmBatch{2, hx, 0, (long long)hx * hx, 0, (long long)R * hx, 0}, 2));
+        k_unfold<<<fold_blocks(half), 256, 0, st>>>(half, Nx, 1, tmp, half, out);
     }
     CUDA_TRY(cudaGetLastError());
     return FOTO_OK;
@@ -218,7 +359,7 @@ int launch_dct_xy(cudaStream_t st, const DctTables &tb, int nplanes, int Ny, int
 int launch_dct_t_solve(cudaStream_t st, const DctTables &tb, int Nt, int ny_loc, int Nx, int y_off, double r, double eps,
                        const double *in, double *out)
 {
-    FOTO_TRY(t_solve(st, tb, Nt, ny_loc, Nx, tb.lam_y + y_off, r, eps, in, out));
+    FOTO_TRY(t_solve(st, tb, Nt, ny_loc, Nx, (tb.split ? tb.lam_yp : tb.lam_y) + y_off, r, eps, in, out));
     CUDA_TRY(cudaGetLastError());
     return FOTO_OK;
 }
@@ -229,7 +370,7 @@ int launch_poisson_dct(cudaStream_t st, const DctTables &tb, int Nt, int Ny, int
                        const double *F, double *phi, double *w0, double *w1)
 {
     FOTO_TRY(launch_dct_xy(st, tb, Nt, Ny, Nx, F, w1, w0, 0));
-    FOTO_TRY(t_solve(st, tb, Nt, Ny, Nx, tb.lam_y, r, eps, w1, w0));
+    FOTO_TRY(t_solve(st, tb, Nt, Ny, Nx, tb.split ? tb.lam_yp : tb.lam_y, r, eps, w1, w0));
     FOTO_TRY(launch_dct_xy(st, tb, Nt, Ny, Nx, w0, phi, w1, 1));
     CUDA_TRY(cudaGetLastError());
     return FOTO_OK;

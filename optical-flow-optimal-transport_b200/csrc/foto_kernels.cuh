@@ -109,7 +109,13 @@ struct DctTables {              // device pointers, owned by the context, valid 
     double *base = nullptr;     // one allocation holding everything below
     double *Cx = nullptr, *CxT = nullptr, *Cy = nullptr, *CyT = nullptr, *Ct = nullptr, *CtT = nullptr;
     double *lam_x = nullptr, *lam_y = nullptr, *lam_t = nullptr;
+    // even / odd folded transforms (Nx and Ny multiples of 4): Ex[b][j][i] = Cx[2j+b][i] for i < Nx/2, ExT its transposes,
+    // the same for y, and the eigenvalues in the permuted spectrum order (even frequencies, then odd)
+    bool split = false;
+    double *Ex = nullptr, *ExT = nullptr, *Ey = nullptr, *EyT = nullptr, *lam_xp = nullptr, *lam_yp = nullptr;
 };
+void dct_host_folded(int n, const std::vector<double> &C, const std::vector<double> &lam, std::vector<double> &E,
+                     std::vector<double> &ET, std::vector<double> &lam_p);
 void dct_host_tables(int n, std::vector<double> &C, std::vector<double> &Ct, std::vector<double> &lam);
 int launch_poisson_dct(cudaStream_t st, const DctTables &tb, int Nt, int Ny, int Nx, double r, double eps,
                        const double *F, double *phi, double *w0, double *w1);

@@ -15,7 +15,10 @@ solver that needs no per-CG-iteration collective.  Every field value is computed
 as on one GPU, so the gathered result is bit-identical to `foto_b200.solve(..., backend=POISSON_DCT_EXACT)`
 whenever the outer-iteration count agrees (the criterion is summed in a different order).
 
-The product path needs a GPU per rank; `plan()` (pure Python) is what the CPU tests cover.
+The product path needs a GPU per rank and the NCCL back-end.  With a gloo process group (which cannot move CUDA
+tensors point to point) the same exchanges are staged through host memory: slower, but it lets two ranks share ONE
+GPU, which is how the 2-rank bit-identity test runs on a single-GPU box.  `plan()` (pure Python) is what the CPU
+tests cover.
 """
 import math
 
@@ -44,6 +47,7 @@ class SlabSolver:
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.Nt, self.Nx, self.Ny, self.P = int(Nt), int(Nx), int(Ny), int(Nx) * int(Ny)
+        self.staged = dist.is_initialized() and dist.get_backend() != "nccl"      # gloo: exchanges go through host memory
         self.geom = plan(self.Nt, self.Ny, self.world)
         self.n0, self.n1 = self.geom["t"][self.rank]
         self.y0, self.y1 = self.geom["y"][self.rank]
@@ -72,16 +76,34 @@ class SlabSolver:
         if self.world == 1:
             return
         dist, L = self.dist, self.nloc
-        ops = []
+        ops, back = [], []
+
+        def snd(t, peer):
+            ops.append(dist.P2POp(dist.isend, t.cpu() if self.staged else t, peer))
+
+        def rcv(t, peer):
+            buf = self.torch.empty(t.shape, dtype=t.dtype) if self.staged else t
+            ops.append(dist.P2POp(dist.irecv, buf, peer))
+            if self.staged:
+                back.append((t, buf))
+
         for f in fields:
             if self.rank > 0:
-                ops.append(dist.P2POp(dist.isend, f[1], self.rank - 1))
-                ops.append(dist.P2POp(dist.irecv, f[0], self.rank - 1))
+                snd(f[1], self.rank - 1); rcv(f[0], self.rank - 1)
             if self.rank < self.world - 1:
-                ops.append(dist.P2POp(dist.isend, f[L], self.rank + 1))
-                ops.append(dist.P2POp(dist.irecv, f[L + 1], self.rank + 1))
+                snd(f[L], self.rank + 1); rcv(f[L + 1], self.rank + 1)
         for w in dist.batch_isend_irecv(ops):
             w.wait()
+        for t, buf in back:
+            t.copy_(buf)
+
+    def _a2a(self, out, inp, out_split, in_split):
+        if not self.staged:
+            self.dist.all_to_all_single(out, inp, out_split, in_split)
+            return
+        host = self.torch.empty(out.numel(), dtype=out.dtype)
+        self.dist.all_to_all_single(host, inp.cpu(), out_split, in_split)
+        out.copy_(host)
 
     def _to_y_slabs(self, A, B):
         """A: [L, Ny, Nx] (my planes, all rows) -> B: [Nt, nyl, Nx] (all planes, my rows)."""
@@ -93,7 +115,7 @@ class SlabSolver:
         self.ctx.slab_pack(0, self.nloc, self.Ny, self.Nx, self.world, A.data_ptr(), self.xbuf.data_ptr())   # one gather kernel
         in_split = [self.nloc * (y1 - y0) * self.Nx for (y0, y1) in self.geom["y"]]
         out_split = [(n1 - n0) * self.nyl * self.Nx for (n0, n1) in self.geom["t"]]
-        dist.all_to_all_single(B.view(-1), self.xbuf, out_split, in_split)   # rank order = plane order
+        self._a2a(B.view(-1), self.xbuf, out_split, in_split)                 # rank order = plane order
 
     def _to_t_slabs(self, B, A):
         """B: [Nt, nyl, Nx] -> A: [L, Ny, Nx]."""
@@ -103,7 +125,7 @@ class SlabSolver:
             return
         in_split = [(n1 - n0) * self.nyl * self.Nx for (n0, n1) in self.geom["t"]]      # contiguous plane ranges of B
         out_split = [self.nloc * (y1 - y0) * self.Nx for (y0, y1) in self.geom["y"]]
-        dist.all_to_all_single(self.xbuf, B.view(-1), out_split, in_split)
+        self._a2a(self.xbuf, B.view(-1), out_split, in_split)
         self.ctx.slab_pack(1, self.nloc, self.Ny, self.Nx, self.world, self.xbuf.data_ptr(), A.data_ptr())   # one scatter kernel
 
     # ------------------------------------------------------------------ solve
@@ -129,9 +151,11 @@ class SlabSolver:
             ctx.dct_xy(self.A.data_ptr(), self.phi[1].data_ptr(), self.tmp.data_ptr(), L, Nt, Ny, Nx, True)
             self._halo([self.phi])
             ctx.slab_prox(self.phi[1].data_ptr(), mu0, q0, self.cs, r, Nt, self.n0, L, Nx, Ny, self.sums.data_ptr())
+            sums = self.sums
             if self.world > 1:
-                dist.all_reduce(self.sums)
-            num, den = (float(x) for x in self.sums.tolist())
+                sums = self.sums.cpu() if self.staged else self.sums
+                dist.all_reduce(sums)
+            num, den = (float(x) for x in sums.tolist())
             prev, crit = crit, math.sqrt(num / (den + 1e-10))          # benamou_brenier.py:246-251
             trace.append(crit)
             if crit <= convergence_tol:
@@ -144,7 +168,7 @@ class SlabSolver:
         if self.world > 1:
             sizes = [(n1 - n0) * P for (n0, n1) in self.geom["t"]]
             parts = [torch.empty(s, dtype=torch.float64, device=self.dev) for s in sizes] if self.rank == 0 else None
-            dist.gather(own.view(-1), parts, dst=0) if len(set(sizes)) == 1 else self._gather_uneven(own.view(-1), parts, sizes)
+            self._gather_uneven(own.view(-1), parts, sizes) if (self.staged or len(set(sizes)) > 1) else dist.gather(own.view(-1), parts, dst=0)
             if self.rank != 0:
                 return None, None, None, info
             full = torch.cat(parts)
@@ -160,6 +184,9 @@ class SlabSolver:
         if self.rank == 0:
             parts[0].copy_(mine)
             for g in range(1, self.world):
-                dist.recv(parts[g], src=g)
+                buf = self.torch.empty(sizes[g], dtype=mine.dtype) if self.staged else parts[g]
+                dist.recv(buf, src=g)
+                if self.staged:
+                    parts[g].copy_(buf)
         else:
-            dist.send(mine, dst=0)
+            dist.send(mine.cpu() if self.staged else mine, dst=0)

@@ -351,6 +351,26 @@ def test_stepA_dct_exact_solves_the_system(tag):
     assert 1e-9 < relerr(phi, g[f"{tag}/phi"]) < 1e-3
 
 
+@pytest.mark.parametrize("h,w,Nt", [(48, 64, 5), (388, 584, 4), (132, 260, 3)])
+def test_dct_folded_transforms_equal_dense(h, w, Nt, monkeypatch):
+    """Nx, Ny multiples of 4: the x and y transforms use the even / odd symmetry of the DCT matrix (half the flops, spectrum
+    in permuted order).  Same Poisson solution as the dense transforms (FOTO_DCT_DENSE=1) to rounding."""
+    rng = np.random.default_rng(h * w)
+    N = Nt * h * w
+    mu, q = rng.standard_normal(3 * N), rng.standard_normal(3 * N)
+    rho0, rhoT = rng.random(h * w), rng.random(h * w)
+    res = {}
+    for dense in ("1", None):
+        if dense: monkeypatch.setenv("FOTO_DCT_DENSE", dense)
+        else: monkeypatch.delenv("FOTO_DCT_DENSE", raising=False)
+        res[dense] = foto_b200.stepA(mu, q, rho0, rhoT, 1.0, 1e-3, Nt, w, h, backend=foto_b200.POISSON_DCT_EXACT)[0]
+    assert relerr(res[None], res["1"]) < 1e-13
+    phi = res[None]
+    L = foto_b200.op_apply("laplacian_st", "N", Nt, w, h, 1, 1, 1, phi)
+    F = foto_b200.rhs(mu, q, rho0, rhoT, 1.0, Nt, w, h)
+    assert np.linalg.norm((-L + 1e-3 * phi) - F) < 1e-11 * np.linalg.norm(F)
+
+
 def test_dct_exact_full_size_matches_tight_cg():
     g = load_golden("foto_388x584")
     h, w, Nt = map(int, g["dims"])
@@ -546,6 +566,21 @@ def test_slab_two_ranks_bit_identical(ranks, h, w, Nt):
     import json
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert res["bit_identical"] and res["outer"] == res["single_gpu_outer"]
+
+
+@pytest.mark.parametrize("ranks,h,w,Nt", [(2, 48, 64, 5), (3, 61, 83, 7)])
+def test_slab_ranks_share_one_gpu_bit_identical(ranks, h, w, Nt):
+    """The same decomposition with every rank on GPU 0 (gloo group, exchanges staged through the host): runs on a
+    single-GPU box, same kernels, same slab geometry, uneven splits with 3 ranks."""
+    import json
+    import subprocess
+    from conftest import ROOT
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ranks}", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "tools", "run_slab.py"), str(h), str(w), str(Nt), "6", "--check", "--one-gpu"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["bit_identical"] and res["outer"] == res["single_gpu_outer"] and res["ranks"] == ranks
 
 
 def test_gn_large_image_streaming_property(cg_variant):

@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
 """Time-slab FOTO solve of ONE volume over the ranks of a torchrun job (config 5 shape, scaled by args).
     python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 tools/run_slab.py H W NT MAX_IT [--check]
---check: rank 0 also solves the volume alone (dct_exact) and requires bit-identical u, v, m."""
+--check: rank 0 also solves the volume alone (dct_exact) and requires bit-identical u, v, m.
+--one-gpu: every rank uses GPU 0 and the process group is gloo (exchanges staged through the host): the 2-rank
+           decomposition checked on a single-GPU box."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "optical-flow-optimal-transport_b200"))
@@ -12,8 +14,13 @@ from foto_b200 import synth, slab
 h, w, Nt, max_it = (int(x) for x in sys.argv[1:5])
 check = "--check" in sys.argv
 rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+one_gpu = "--one-gpu" in sys.argv
+if one_gpu:
+    local = 0
 torch.cuda.set_device(local)
-if world > 1:
+if world > 1 and one_gpu:
+    dist.init_process_group("gloo")
+elif world > 1:
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 dev = torch.device("cuda", local)
@@ -29,7 +36,7 @@ t0 = time.perf_counter()
 u, v, m, info = s.solve(d0, d1, **kw)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
-out = {"mode": "time-slab", "ranks": world, "grid": [Nt, h, w], "cells": Nt * h * w, "planes_per_rank": [b - a for a, b in s.geom["t"]],
+out = {"mode": "time-slab" + (" (one GPU, gloo, host-staged exchanges)" if one_gpu else ""), "ranks": world, "grid": [Nt, h, w], "cells": Nt * h * w, "planes_per_rank": [b - a for a, b in s.geom["t"]],
        "outer": info["n_outer"], "seconds": dt, "outer_iters_per_s": info["n_outer"] / dt, "crit_last": float(info["crit"][-1])}
 if rank == 0 and check:
     ctx = foto_b200.Context(local)
