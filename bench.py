@@ -334,13 +334,15 @@ def run_b200(args):
             onchip["ncu_source"] = t["source"]
             if "lsu_shared_wavefronts_per_iteration_per_sm" in t:
                 wf = t["lsu_shared_wavefronts_per_iteration_per_sm"]; ar = t["allreduce_floor_cycles"]
+                cyc = onchip["cycles_per_cg_iteration"]
                 onchip["bounds"] = {
                     "shared_memory_pipe": {"wavefronts_per_iteration_per_sm": wf, "peak_wavefronts_per_clk": 1,
-                                           "frac_of_iteration": wf / onchip["cycles_per_cg_iteration"]},
-                    "grid_allreduce_floor_cycles": ar,
-                    "frac_of_serial_floor": (wf + ar) / onchip["cycles_per_cg_iteration"],
-                    "note": "an iteration cannot be shorter than its shared-memory wavefronts (1 per clock per SM) plus one grid "
-                            "all-reduce (two L2 traversals, tools/ubench_allreduce2.cu); frac_of_serial_floor = that floor / measured cycles"}
+                                           "frac_of_iteration": wf / cyc},
+                    "grid_allreduce_floor_cycles": ar, "grid_allreduce_floor_frac_of_iteration": ar / cyc,
+                    "note": "critical path of an iteration = stencil + block reduce + one grid all-reduce (two L2 traversals across the "
+                            "dies, tools/ubench_allreduce2.cu) + vector update; the x update and the tile-edge export / import run in "
+                            "the shadow of the all-reduce (profiles/r2_onchip_phase_cycles.log: 3 113 + 4 272 + 2 343 cycles); the "
+                            "shared-memory pipe (ncu wavefronts, 1 per clock per SM) is the busiest unit"}
         line = {
             "metric": "FOTO frame-pairs/s at 388x584", "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
