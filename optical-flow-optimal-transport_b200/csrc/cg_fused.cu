@@ -408,7 +408,8 @@ __global__ void k_fill2_u64(unsigned long long *p, int n, unsigned long long v, 
 // stencil window 6 NT); Nt = 4 is the CLI default and the benchmark configuration
 struct Shape { int nt, ypt, threads; bool xg; const void *unit, *general; };
 #define FOTO_FUSED_SHAPE(NT, YPT, T, XG) {NT, YPT, T, XG, (const void *)cg_fused_kernel<T, NT, YPT, true, XG>, (const void *)cg_fused_kernel<T, NT, YPT, false, XG>}
-// listed fastest first per Nt.  Nt = 4: 448 threads (14 warps: 2 % faster than 16 at 388x584x4, 7 168 cell slots), 512
+// listed fastest first per Nt.  Nt = 4 at 388x584 (us per iteration, this round's kernel): 448 threads x 16 slots 4.76, 384 x 20
+// (168 registers, no spills) 4.78, 512 x 16 4.89, 320 x 24 5.11.  448 threads (14 warps, 7 168 cell slots), 512
 // threads (8 192), then 384 threads x 24 slots with x in global memory (9 216; 576 threads x 16 slots are capped at 96
 // registers and spill: 10.2 against 7.7 us per iteration at 480x640x4)
 const Shape kShapes[] = {FOTO_FUSED_SHAPE(2, 8, 512, false), FOTO_FUSED_SHAPE(3, 5, 512, false), FOTO_FUSED_SHAPE(4, 4, 448, false),
@@ -431,8 +432,10 @@ Plan make_plan(OnchipScratch &d, int device, int Nt, int Ny, int Nx)
         if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return best;
         d.num_sms = prop.multiProcessorCount; d.smem_optin = prop.sharedMemPerBlockOptin;
     }
+    int force_shape = -1;                                // FOTO_FUSED_SHAPE=index into kShapes (experiments)
+    if (const char *e = getenv("FOTO_FUSED_SHAPE")) force_shape = atoi(e);
     for (int shape = 0; shape < kNumShapes && !best.ok; shape++) {
-    if (kShapes[shape].nt != Nt) continue;
+    if (kShapes[shape].nt != Nt || (force_shape >= 0 && shape != force_shape)) continue;
     const int kNT = Nt, kYPT = kShapes[shape].ypt, kThreads = kShapes[shape].threads;
     const int xslots = kShapes[shape].xg ? 1 : 2;       // private shared-memory arrays of kNT*kYPT*kThreads doubles
     best.shape = shape;
