@@ -48,7 +48,9 @@ using namespace gsync;
 struct Geom {
     int gy, gx, maxlen;
     double *edges;                 // [2 (iteration parity)][ncta][4 (N,S,W,E)][NT * maxlen] tile-edge values of w, LSB = tag
-    unsigned long long *slots;     // all-reduce slots (grid_sync.cuh)
+    unsigned long long *slots;     // all-reduce words: kGranules 2 KB granules + the placement record (see place_allreduce)
+    unsigned int launch_seq;       // distinguishes the placement broadcast of this launch from the previous one's
+    unsigned int force_choice;     // experiments: granules given by FOTO_AR_PLACE=a,b,t (bit 31 set), bit 30: print the classification
     long long *prof;
 };
 
@@ -59,6 +61,127 @@ constexpr int kHaloPerThread = 4;
 __device__ __forceinline__ void red_add_f64(double *p, double v)
 {
     asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// ---- where the all-reduce words live.  B200 is two dies of 74 SMs with the L2 split between them, and the home of an
+// address changes every 2 KB.  A word that one SM stores and another polls becomes visible in ~480 cycles when its home is
+// on the die of both SMs and in ~900 when it is not (tools/ubench_die.cu); for the all-reduce that is 4.75 against up to
+// 5.27 us per CG iteration depending on where cudaMalloc happened to put the buffer (profiles/r2_allreduce_placement.md:
+// best with the partial slots AND the totals on the root's die).  So the buffer is kGranules 2 KB granules, the root
+// classifies them once by a self ping-pong (store a value, poll it back: ~300 cycles on its own die, ~720 on the other),
+// keeps the partial slots and the totals in granules of its own die, remembers the choice per SM id, and tells the
+// other CTAs at the start of every launch.
+constexpr int kGranules = 32, kGranWords = 256, kSlotsPerGran = 128;       // 16-byte slots
+constexpr int kPlaceOff = kGranules * kGranWords;       // words: [0] choice of this launch, [1] cached choice, [2] its SM id + 1
+constexpr int kFusedSlotWords = kPlaceOff + 16;
+
+struct Placement { unsigned long long *part_a, *part_b, *tot; };          // CTAs 0..127 / 128..255 / totals
+
+__device__ __forceinline__ Placement placement_of(unsigned long long *base, unsigned long long choice)
+{
+    Placement p;
+    p.part_a = base + (choice & 255) * kGranWords;
+    p.part_b = base + ((choice >> 8) & 255) * kGranWords;
+    p.tot = base + ((choice >> 16) & 255) * kGranWords;
+    return p;
+}
+
+// thread 0 of every CTA, before the first all-reduce
+__device__ Placement place_allreduce(unsigned long long *base, unsigned int seq, bool root, bool *timed_out, unsigned int force)
+{
+    unsigned long long *rec = base + kPlaceOff;
+    unsigned long long choice;
+    if (root) {
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        choice = ld_relaxed_u64(rec + 1);
+        if (ld_relaxed_u64(rec + 2) != (unsigned long long)smid + 1 || (force & 0x40000000u)) {
+            int t[kGranules], lo = 1 << 30, hi = 0;
+            for (int g = 0; g < kGranules; g++) {
+                unsigned long long *w = base + g * kGranWords + 2 * kSlotsPerGran - 2;      // last slot of the granule: never used below 128 CTAs
+                int m = 1 << 30;
+                for (int rep = 0; rep < 5; rep++) {
+                    const unsigned long long v = 0xC0DE0000ull + (unsigned long long)rep * 2 + 1;        // odd: reads as "not written" afterwards
+                    const long long c0 = clock64();
+                    st_relaxed_u64(w, v);
+                    while (ld_relaxed_u64(w) != v && clock64() - c0 < 1000000) { }
+                    const int d = (int)(clock64() - c0);
+                    m = d < m ? d : m;
+                }
+                st_relaxed_u64(w, ~0ull);
+                t[g] = m; lo = m < lo ? m : lo; hi = m > hi ? m : hi;
+            }
+            if (force & 0x40000000u) {
+                printf("root smid %u, self ping-pong cycles per granule:", smid);
+                for (int g = 0; g < kGranules; g++) printf(" %d", t[g]);
+                printf("\n");
+            }
+            int pick[3] = {0, 1, 2}, n = 0;
+            for (int g = 0; g < kGranules && n < 3; g++) if (2 * t[g] <= lo + hi) pick[n++] = g;
+            choice = (unsigned long long)pick[0] | ((unsigned long long)pick[1] << 8) | ((unsigned long long)pick[2] << 16);
+            st_relaxed_u64(rec + 1, choice);
+            st_relaxed_u64(rec + 2, (unsigned long long)smid + 1);
+        }
+        if (force & 0x80000000u) choice = force & 0xFFFFFFu;
+        choice = (choice & 0xFFFFFFull) | ((unsigned long long)seq << 32);
+        st_relaxed_u64(rec, choice);
+    } else {
+        const long long c0 = clock64();
+        do { choice = ld_relaxed_u64(rec); } while ((unsigned int)(choice >> 32) != seq && clock64() - c0 < kWatchdogCycles);
+        if ((unsigned int)(choice >> 32) != seq) { *timed_out = true; choice = 0x020100ull; }      // the root never showed up
+    }
+    return placement_of(base, choice);
+}
+
+// the all-reduce of grid_sync.cuh (two values, tagged words) with explicit addresses
+__device__ __forceinline__ void arrive2(unsigned long long *slot, unsigned int gen, const double *v, bool abort = false)
+{
+    const unsigned long long par = (unsigned long long)(gen & 1u);
+    st_relaxed_v2(slot, abort ? (kAbort | par) : tagged(v[0], gen), abort ? (kAbort | par) : tagged(v[1], gen));
+}
+__device__ __forceinline__ void root2(const Placement &pl, unsigned int gen, int ncta, int lane)
+{
+    constexpr int PER_LANE = 5;
+    const long long t0 = clock64();
+    const unsigned long long par = (unsigned long long)(gen & 1u);
+    bool abort = false;
+    unsigned long long w[PER_LANE][2];
+    bool ready;
+    do {
+#pragma unroll
+        for (int k = 0; k < PER_LANE; k++) {
+            int b = k * 32 + lane; if (b >= ncta) b = 0;
+            ld_relaxed_v2((b < kSlotsPerGran ? pl.part_a : pl.part_b) + 2 * (b & (kSlotsPerGran - 1)), w[k][0], w[k][1]);
+        }
+        ready = true;
+#pragma unroll
+        for (int k = 0; k < PER_LANE; k++) ready = ready & ((w[k][0] & 1ull) == par) & ((w[k][1] & 1ull) == par);
+        if (!ready && clock64() - t0 > kWatchdogCycles) { abort = true; break; }
+    } while (!ready);
+    double tot[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < PER_LANE; k++)
+        if (k * 32 + lane < ncta) {
+            tot[0] += __longlong_as_double((long long)w[k][0]); tot[1] += __longlong_as_double((long long)w[k][1]);
+            abort = abort || is_abort(w[k][0]) || is_abort(w[k][1]);
+        }
+    tot[0] = warp_sum(tot[0]); tot[1] = warp_sum(tot[1]);
+    abort = __any_sync(0xffffffffu, abort);
+    if (lane == 0) st_relaxed_v2(pl.tot, abort ? (kAbort | par) : tagged(tot[0], gen), abort ? (kAbort | par) : tagged(tot[1], gen));
+}
+__device__ __forceinline__ bool wait2(const unsigned long long *tot, unsigned int gen, double *out)
+{
+    const long long t0 = clock64();
+    const unsigned long long par = (unsigned long long)(gen & 1u);
+    unsigned long long a, b;
+    bool ready, ok = true;
+    do {
+        ld_relaxed_v2(tot, a, b);
+        ready = ((a & 1ull) == par) & ((b & 1ull) == par);
+        if (!ready && clock64() - t0 > 2 * kWatchdogCycles) { ok = false; break; }
+    } while (!ready);
+    out[0] = __longlong_as_double((long long)a); out[1] = __longlong_as_double((long long)b);
+    return ok && !is_abort(a) && !is_abort(b);
 }
 
 // XG: x lives in global memory (L2 resident) instead of shared memory: the large variant (384 threads x 24 cell slots =
@@ -211,6 +334,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
     const bool prof = g.prof != nullptr && tid == 0;
     long long *sprof = (long long *)(red + 72);           // shared-memory accumulators (thread 0 only)
     if (tid == 0) { for (int k = 0; k < 6; k++) sprof[k] = 0; red[66] = 0.0; red[67] = 0.0; }
+    // all-reduce addresses (only warp 0 uses them): red[68..71] = partial granules a, b, totals, this CTA's slot
+    unsigned long long **arp = (unsigned long long **)(red + 68);
+    if (tid == 0) {
+        bool timed_out = false;
+        const Placement pl = place_allreduce(g.slots, g.launch_seq, cta == 0, &timed_out, g.force_choice);
+        if (timed_out) red[66] = 1.0;
+        arp[0] = pl.part_a; arp[1] = pl.part_b; arp[2] = pl.tot;
+        arp[3] = (cta < kSlotsPerGran ? pl.part_a : pl.part_b) + 2 * (cta & (kSlotsPerGran - 1));
+    }
     auto lap = [&](int k) { if (prof) { long long now = clock64(); sprof[k] += now - tmark; tmark = now; } };
 
     int it = 0, status = a.maxiter;
@@ -272,8 +404,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
             if (tid < 32) {
                 acc[0] = warp_sum(tid < NTHREADS / 32 ? red[tid] : 0.0);
                 acc[1] = warp_sum(tid < NTHREADS / 32 ? red[32 + tid] : 0.0);
-                if (tid == 0) grid_arrive<2>(g.slots, gen, acc);
-                if (cta == 0) grid_root<2>(g.slots, gen, ncta, tid);
+                if (tid == 0) arrive2(arp[3], gen, acc);
+                if (cta == 0) root2(Placement{arp[0], arp[1], arp[2]}, gen, ncta, tid);
             }
         }
         export_edges((unsigned int)it);
@@ -307,7 +439,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
         import_edges();
         lap(1);
         if (tid == 0) {
-            if (!grid_wait<2>(g.slots, gen, red + 64)) red[67] = 1.0;
+            if (!wait2(arp[2], gen, red + 64)) red[67] = 1.0;
         }
         __syncthreads();
         gen++;
@@ -317,9 +449,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
         if (abort) break;
         if (red[66] != 0.0) {                            // import watchdog of this CTA: one more round that tells every CTA
             __syncthreads();
-            if (tid == 0) grid_arrive<2>(g.slots, gen, acc, true);
-            if (cta == 0 && tid < 32) grid_root<2>(g.slots, gen, ncta, tid);
-            if (tid == 0) grid_wait<2>(g.slots, gen, red + 64);
+            if (tid == 0) arrive2(arp[3], gen, acc, true);
+            if (cta == 0 && tid < 32) root2(Placement{arp[0], arp[1], arp[2]}, gen, ncta, tid);
+            if (tid == 0) wait2(arp[2], gen, red + 64);
             abort = true;
             break;
         }
@@ -470,9 +602,9 @@ bool cg_fused_fits(OnchipScratch &s, int device, int Nt, int Ny, int Nx) { retur
 
 void onchip_release(OnchipScratch &s)
 {
-    cudaFree(s.prof); cudaFree(s.fused_edges); cudaFree(s.fused_slots); cudaFree(s.gnf_edges); cudaFree(s.gnf_slots);
+    cudaFree(s.prof); cudaFree(s.fused_edges); cudaFree(s.fused_slots_raw); cudaFree(s.gnf_edges); cudaFree(s.gnf_slots);
     s.prof = nullptr;
-    s.fused_edges = nullptr; s.fused_slots = nullptr; s.fused_edges_bytes = 0;
+    s.fused_edges = nullptr; s.fused_slots = nullptr; s.fused_slots_raw = nullptr; s.fused_edges_bytes = 0;
     s.gnf_edges = nullptr; s.gnf_slots = nullptr; s.gnf_edges_bytes = 0;
 }
 
@@ -486,7 +618,11 @@ int launch_cg_fused(cudaStream_t st, const CgArgs &a, int device, OnchipScratch 
         CUDA_TRY(cudaMalloc((void **)&d.fused_edges, need));
         d.fused_edges_bytes = need;
     }
-    if (!d.fused_slots) CUDA_TRY(cudaMalloc((void **)&d.fused_slots, kSlotWords * sizeof(unsigned long long)));
+    if (!d.fused_slots) {                                // 2 KB aligned granules + the placement record (zeroed once: "nothing cached")
+        CUDA_TRY(cudaMalloc((void **)&d.fused_slots_raw, (kFusedSlotWords + kGranWords) * sizeof(unsigned long long)));
+        d.fused_slots = (unsigned long long *)(((size_t)d.fused_slots_raw + 2047) & ~(size_t)2047);
+        CUDA_TRY(cudaMemsetAsync(d.fused_slots + kPlaceOff, 0, 16 * sizeof(unsigned long long), st));
+    }
     const void *fn = a.rcoef == 1.0 ? kShapes[p.shape].unit : kShapes[p.shape].general;
     if (!d.fused_attr_set) {
         for (int i = 0; i < kNumShapes; i++) {
@@ -497,9 +633,16 @@ int launch_cg_fused(cudaStream_t st, const CgArgs &a, int device, OnchipScratch 
     }
     const int nedge = (int)(need / sizeof(double));
     // all-reduce slots and edge words <- tag 1 ("generations 0 and 1 not yet written")
-    k_fill2_u64<<<((nedge > kSlotWords ? nedge : kSlotWords) + 255) / 256, 256, 0, st>>>(d.fused_slots, kSlotWords, kSlotInit, (unsigned long long *)d.fused_edges, nedge, ~0ull);
+    k_fill2_u64<<<((nedge > kPlaceOff ? nedge : kPlaceOff) + 255) / 256, 256, 0, st>>>(d.fused_slots, kPlaceOff, kSlotInit, (unsigned long long *)d.fused_edges, nedge, ~0ull);
     Geom g;
     g.gy = p.gy; g.gx = p.gx; g.maxlen = p.maxlen; g.edges = d.fused_edges; g.slots = d.fused_slots; g.prof = d.prof;
+    g.launch_seq = ++d.fused_launch_seq;
+    g.force_choice = 0;
+    if (const char *e = getenv("FOTO_AR_PLACE")) {
+        int ga = 0, gb = 1, gt = 2;
+        if (sscanf(e, "%d,%d,%d", &ga, &gb, &gt) == 3) g.force_choice = 0x80000000u | (ga & 31) | ((gb & 31) << 8) | ((gt & 31) << 16);
+    }
+    if (getenv("FOTO_AR_DEBUG") && d.fused_launch_seq == 1) g.force_choice |= 0x40000000u;
     void *args[] = {(void *)&a, (void *)&g};
     CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(p.ncta), dim3(kShapes[p.shape].threads), args, p.smem, st));
     return FOTO_OK;

@@ -92,7 +92,8 @@ struct OnchipScratch {
     size_t smem_optin = 0;
     long long *prof = nullptr;  // 8 cycle counters per CTA (debugging aid, see foto_debug_onchip_prof)
     double *fused_edges = nullptr; size_t fused_edges_bytes = 0;   // cg_fused.cu
-    unsigned long long *fused_slots = nullptr;
+    unsigned long long *fused_slots = nullptr, *fused_slots_raw = nullptr;
+    unsigned int fused_launch_seq = 0;
     bool fused_attr_set = false;
     double *gnf_edges = nullptr; size_t gnf_edges_bytes = 0;    // gn_fused.cu
     unsigned long long *gnf_slots = nullptr;
