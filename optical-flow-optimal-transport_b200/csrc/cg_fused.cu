@@ -36,6 +36,8 @@
 // from registers inside the unrolled update costs the edge warps 1 500 cycles.)
 // Shadow of the all-reduce of iteration k: export of w_k's edges, the whole x += alpha_{k-1} p_{k-1}, import of the
 // neighbours' edges into registers.
+#include <type_traits>
+
 #include "foto_kernels.cuh"
 #include "grid_sync.cuh"
 
@@ -363,23 +365,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
     for (; it < a.maxiter; it++) {
         // ---- w = A r (csr_matvec order), partial r.r and r.w
         double acc[2] = {0.0, 0.0};
-        if (nval > 0) {
+        // FULL: every thread of the warp owns YPT rows -> no per-row branch, the rolling window is renamed instead of moved
+        // (48 register moves less per thread and iteration); warps of the last thread row of a tile take the general path
+        auto stencil = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
             double up[NT], cur[NT], nxt[NT];             // rolling window over the owned rows, all NT levels
             const double *pb = rs + fresh(sb);
 #pragma unroll
             for (int t = 0; t < NT; t++) { up[t] = pb[t * plane - PX]; cur[t] = pb[t * plane]; }
 #pragma unroll
             for (int jy = 0; jy < YPT; jy++) {
-                if (jy < nval) {
+                if (FULL || jy < nval) {
 #pragma unroll
                     for (int t = 0; t < NT; t++) nxt[t] = pb[t * plane + (jy + 1) * PX];
                     const int ym = (jy == jTop) + (jy == jBot);
+                    double dgb = dg_tb, dgi = dg_ti;
+                    if (ym) { dgb = dtab[2 - xmiss - ym]; dgi = dtab[3 - xmiss - ym]; }      // rows on the global y boundary only
 #pragma unroll
                     for (int t = 0; t < NT; t++) {
                         const double *px = pb + t * plane + jy * PX;
                         const bool tb = t == 0 || t == NT - 1;
-                        double dg = tb ? dg_tb : dg_ti;
-                        if (ym) dg = dtab[(tb ? 5 : 6) - xmiss - ym - 3];
+                        const double dg = tb ? dgb : dgi;
                         const double c = cur[t];
                         double s = 0.0;
                         if (UNIT) {                      // r == 1: products with -1.0 are exact negations
@@ -403,7 +409,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
                     for (int t = 0; t < NT; t++) { up[t] = cur[t]; cur[t] = nxt[t]; }
                 }
             }
-        }
+        };
+#ifdef FOTO_AB_STENCIL_GENERAL
+        if (nval > 0) stencil(std::false_type{});
+#else
+        if (__all_sync(0xffffffffu, nval == YPT)) stencil(std::true_type{});
+        else if (nval > 0) stencil(std::false_type{});
+#endif
         lap(0);
         // ---- the one all-reduce; in its shadow: export of the edges of w, x update of the previous iteration,
         //      import of the neighbours' edges of w (into registers)
@@ -484,17 +496,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
         const double dk = del - (beta * beta) * d_prev;
         const double alpha = gam / dk;
         // ---- p = r + beta p, s = w + beta s, r -= alpha s on the owned cells ...
+        // (a branch-free copy of this loop for warps whose threads all own YPT rows, as in the stencil, is slower: 4.83
+        // against 4.72 us per iteration, A/B on one box)
+        {
+            double *pr[NT];
 #pragma unroll
-        for (int jy = 0; jy < YPT; jy++) {
-            if (jy < nval) {
+            for (int t = 0; t < NT; t++) pr[t] = rs + fresh(sb) + t * plane;
+            const double *wp = ws + tid;
 #pragma unroll
-                for (int t = 0; t < NT; t++) {
-                    const int j = t * YPT + jy, si = fresh(sb) + t * plane + jy * PX;
-                    const double rv = rs[si], wv = ws[j * NTHREADS + tid];
-                    const double sv = sj[j] * beta + wv;
-                    pj[j] = pj[j] * beta + rv;
-                    sj[j] = sv;
-                    rs[si] = rv - alpha * sv;
+            for (int jy = 0; jy < YPT; jy++) {
+                if (jy < nval) {
+#pragma unroll
+                    for (int t = 0; t < NT; t++) {
+                        const int j = t * YPT + jy;
+                        const double rv = pr[t][0], wv = wp[j * NTHREADS];
+                        const double sv = sj[j] * beta + wv;
+                        pj[j] = pj[j] * beta + rv;
+                        sj[j] = sv;
+                        pr[t][0] = rv - alpha * sv;
+                        pr[t] += PX;
+                    }
                 }
             }
         }
