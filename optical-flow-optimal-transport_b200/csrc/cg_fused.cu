@@ -36,8 +36,6 @@
 // from registers inside the unrolled update costs the edge warps 1 500 cycles.)
 // Shadow of the all-reduce of iteration k: export of w_k's edges, the whole x += alpha_{k-1} p_{k-1}, import of the
 // neighbours' edges into registers.
-#include <type_traits>
-
 #include "foto_kernels.cuh"
 #include "grid_sync.cuh"
 
@@ -365,17 +363,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
     for (; it < a.maxiter; it++) {
         // ---- w = A r (csr_matvec order), partial r.r and r.w
         double acc[2] = {0.0, 0.0};
-        // FULL: every thread of the warp owns YPT rows -> no per-row branch, the rolling window is renamed instead of moved
-        // (48 register moves less per thread and iteration); warps of the last thread row of a tile take the general path
-        auto stencil = [&](auto full_tag) {
-            constexpr bool FULL = decltype(full_tag)::value;
+        // (a branch-free copy of this block for warps whose threads all own YPT rows saves 48 register moves per thread and
+        // 160 in-kernel cycles per iteration under the phase counters, but the plain build is 1 % slower with it: A/B on one box)
+        if (nval > 0) {
             double up[NT], cur[NT], nxt[NT];             // rolling window over the owned rows, all NT levels
             const double *pb = rs + fresh(sb);
 #pragma unroll
             for (int t = 0; t < NT; t++) { up[t] = pb[t * plane - PX]; cur[t] = pb[t * plane]; }
 #pragma unroll
             for (int jy = 0; jy < YPT; jy++) {
-                if (FULL || jy < nval) {
+                if (jy < nval) {
 #pragma unroll
                     for (int t = 0; t < NT; t++) nxt[t] = pb[t * plane + (jy + 1) * PX];
                     const int ym = (jy == jTop) + (jy == jBot);
@@ -409,13 +406,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
                     for (int t = 0; t < NT; t++) { up[t] = cur[t]; cur[t] = nxt[t]; }
                 }
             }
-        };
-#ifdef FOTO_AB_STENCIL_GENERAL
-        if (nval > 0) stencil(std::false_type{});
-#else
-        if (__all_sync(0xffffffffu, nval == YPT)) stencil(std::true_type{});
-        else if (nval > 0) stencil(std::false_type{});
-#endif
+        }
         lap(0);
         // ---- the one all-reduce; in its shadow: export of the edges of w, x update of the previous iteration,
         //      import of the neighbours' edges of w (into registers)
