@@ -1086,6 +1086,25 @@ extern "C" int foto_slab_prox_dev(foto_ctx *c, const double *phi, double *mu, do
     return FOTO_OK;
 }
 
+// One step of the reference's truncated CG on a time slab (cg_slab.cu); the caller issues the collectives in between.
+extern "C" int foto_slab_cg_dev(foto_ctx *c, int op, int gNt, int n0, int nloc, int Ny, int Nx, double r, double eps, double rtol, int it,
+                                int maxiter, const double *d_b, double *d_x, double *d_r, double *d_p_old, double *d_p_new, double *d_q,
+                                double *d_state)
+{
+    if (!c || !d_state || gNt < 2 || nloc < 1 || n0 < 0 || n0 + nloc > gNt || Nx < 2 || Ny < 2) { set_error("foto_slab_cg_dev: bad argument"); return FOTO_ERR_ARG; }
+    if ((unsigned long long)Nx * Ny * ((unsigned long long)nloc + 2) >= (1ull << 32)) { set_error("foto_slab_cg_dev: slab too large"); return FOTO_ERR_ARG; }
+    if ((op == 0 && (!d_b || !d_x || !d_r || !d_p_old)) || (op == 3 && (!d_r || !d_p_old || !d_p_new || !d_q)) ||
+        (op == 5 && (!d_x || !d_r || !d_p_new || !d_q))) { set_error("foto_slab_cg_dev: NULL argument"); return FOTO_ERR_ARG; }
+    static_assert(2 * kMaxVals * kMaxBlocks >= 148 * 8, "partials buffer");
+    FOTO_TRY(ctx_bind(c));
+    FOTO_TRY(launch_cg_slab(c->stream, op, gNt, n0, nloc, Ny, Nx, r, eps, rtol, it, maxiter, d_b, d_x, d_r, d_p_old, d_p_new, d_q,
+                            c->sync_partials, d_state));
+    c->stats.launches++;
+    return FOTO_OK;
+}
+
+extern "C" int foto_slab_cg_state_words(void) { return (int)cg_slab_state_words(); }
+
 extern "C" int foto_dct_xy_dev(foto_ctx *c, const double *in, double *out, double *tmp, int nplanes, int gNt, int Ny, int Nx,
                                int inverse)
 {

@@ -125,6 +125,13 @@ int launch_dct_xy(cudaStream_t st, const DctTables &tb, int nplanes, int Ny, int
 int launch_dct_t_solve(cudaStream_t st, const DctTables &tb, int Nt, int ny_loc, int Nx, int y_off, double r, double eps,
                        const double *in, double *out);
 
+// ---- truncated CG over time slabs, stepwise (cg_slab.cu): the collectives between the steps belong to the caller
+size_t cg_slab_state_words();
+size_t cg_slab_partial_words();
+int launch_cg_slab(cudaStream_t st, int op, int gNt, int n0, int nloc, int Ny, int Nx, double rcoef, double eps, double rtol, int it,
+                   int maxiter, const double *b, double *x, double *r, double *p_old, double *p_new, double *q, double *partials,
+                   double *state);
+
 // ---- Gennert-Negahdaripour (gn_kernels.cu) ---------------------------------------------
 // K5: fx, fy (central, zero on the border), ft, Jacobi inverse diagonal, right-hand side
 void launch_gn_coeffs(cudaStream_t st, int w, int h, const double *f1, const double *f2, double alpha,

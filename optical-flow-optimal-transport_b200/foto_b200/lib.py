@@ -28,7 +28,7 @@ EXPORTS = [
     "foto_solve_batch", "foto_gn_solve_batch", "foto_pack_flo", "foto_flow_metrics",
     "foto_ctx_set_stream", "foto_slab_rhs_dev", "foto_slab_prox_dev", "foto_dct_xy_dev", "foto_dct_t_solve_dev",
     "foto_flow_dev", "foto_ingest_u8_dev", "foto_pack_flo_dev", "foto_flow_metrics_dev", "foto_warp_dev",
-    "foto_solve_batch_u8", "foto_slab_pack_dev",
+    "foto_solve_batch_u8", "foto_slab_pack_dev", "foto_slab_cg_dev", "foto_slab_cg_state_words",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -394,6 +394,11 @@ class Context:
         vp = C.c_void_p
         _check(lib().foto_dct_t_solve_dev(self._h, vp(d_in), vp(d_out), int(gNt), int(Ny), int(Nx), int(y_off), int(ny_loc),
                                           _d(r), _d(eps)))
+
+    def slab_cg(self, op, gNt, n0, nloc, Ny, Nx, r, eps, rtol, it, maxiter, d_b, d_x, d_r, d_p_old, d_p_new, d_q, d_state):
+        vp = C.c_void_p
+        _check(lib().foto_slab_cg_dev(self._h, int(op), int(gNt), int(n0), int(nloc), int(Ny), int(Nx), _d(r), _d(eps), _d(rtol),
+                                      int(it), int(maxiter), vp(d_b), vp(d_x), vp(d_r), vp(d_p_old), vp(d_p_new), vp(d_q), vp(d_state)))
 
     def slab_pack(self, direction, nloc, Ny, Nx, world, d_in, d_out):
         vp = C.c_void_p

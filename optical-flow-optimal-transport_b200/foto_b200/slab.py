@@ -10,10 +10,15 @@ SURVEY.md section 8(e), second row / BASELINE.json config 5.  Rank g owns the co
   * the two sums of the stopping criterion                                            -- all_reduce
 
 and run the library's slab kernels in between (foto_slab_rhs_dev, foto_dct_xy_dev, foto_dct_t_solve_dev,
-foto_slab_prox_dev on the torch stream).  The Poisson back-end is the exact DCT solve: it is the only
+foto_slab_prox_dev on the torch stream).  The default Poisson back-end is the exact DCT solve: it is the only
 solver that needs no per-CG-iteration collective.  Every field value is computed with the same arithmetic
 as on one GPU, so the gathered result is bit-identical to `foto_b200.solve(..., backend=POISSON_DCT_EXACT)`
 whenever the outer-iteration count agrees (the criterion is summed in a different order).
+
+`poisson="cg_parity"` runs the reference's truncated CG instead (benamou_brenier.py:85 semantics across the ranks,
+foto_slab_cg_dev): per CG iteration one boundary plane of r to each neighbour and two one-word all-reduces; the
+host enqueues iterations ahead and reads the device's `done` flag every 16 iterations.  Same recurrences as the
+one-GPU streaming kernel, dot products summed in another order: 1e-9 agreement unless a CG count flips by one.
 
 The product path needs a GPU per rank and the NCCL back-end.  With a gloo process group (which cannot move CUDA
 tensors point to point) the same exchanges are staged through host memory: slower, but it lets two ranks share ONE
@@ -68,6 +73,7 @@ class SlabSolver:
         self.xbuf = torch.empty(L * P, **f64)                 # all-to-all staging: block of rank g = [L][rows of g][Nx]
         self.sums = torch.zeros(2, **f64)
         self.cs = (L + 2) * P
+        self._cg = None                                       # buffers of the cg_parity back-end, allocated on first use
 
     # ------------------------------------------------------------------ exchanges
     def _halo(self, fields):
@@ -128,8 +134,51 @@ class SlabSolver:
         self._a2a(self.xbuf, B.view(-1), out_split, in_split)
         self.ctx.slab_pack(1, self.nloc, self.Ny, self.Nx, self.world, self.xbuf.data_ptr(), A.data_ptr())   # one scatter kernel
 
+    # ------------------------------------------------------------------ truncated CG over the slabs
+    def _poisson_cg(self, r, eps, rtol=1e-6, maxiter=1000, look=16):
+        """phi (owned planes) <- scipy-cg(A, F, rtol, maxiter) as the reference calls it; returns (iterations, info)."""
+        torch, dist, ctx = self.torch, self.dist, self.ctx
+        L, P = self.nloc, self.P
+        if self._cg is None:
+            f64 = dict(dtype=torch.float64, device=self.dev)
+            from .lib import lib as _lib
+            self._cg = dict(r=torch.zeros((L + 2, P), **f64), p=[torch.zeros((L + 2, P), **f64) for _ in range(2)],
+                            q=torch.empty((L, P), **f64), state=torch.zeros(int(_lib().foto_slab_cg_state_words()), **f64))
+        c = self._cg
+        rr, q, state = c["r"], c["q"], c["state"]
+        x = self.phi[1].data_ptr()
+        state.zero_()
+
+        def step(op, it=0, pold=c["p"][0], pnew=c["p"][1]):
+            ctx.slab_cg(op, self.Nt, self.n0, L, self.Ny, self.Nx, r, eps, rtol, it, maxiter, self.F.data_ptr(), x, rr[1].data_ptr(),
+                        pold[1].data_ptr(), pnew[1].data_ptr(), q.data_ptr(), state.data_ptr())
+
+        def allreduce():
+            if self.world > 1:
+                if self.staged:
+                    v = state[:1].cpu(); dist.all_reduce(v); state[:1].copy_(v)
+                else:
+                    dist.all_reduce(state[:1])
+
+        step(0); allreduce(); step(1)
+        it = 0
+        while it < maxiter:
+            for _ in range(min(look, maxiter - it)):
+                pold, pnew = c["p"][it & 1], c["p"][(it + 1) & 1]
+                step(2, it, pold, pnew)
+                self._halo([rr])
+                step(3, it, pold, pnew); allreduce(); step(4, it, pold, pnew)
+                step(5, it, pold, pnew); allreduce(); step(6, it, pold, pnew)
+                it += 1
+            if float(state[4]) != 0.0:
+                break
+        if float(state[4]) == 0.0:
+            step(7, maxiter)                                  # scipy returns (x, maxiter) without another test
+        st = state.tolist()
+        return int(st[5]), int(st[6])
+
     # ------------------------------------------------------------------ solve
-    def solve(self, rho0, rhoT, r=1.0, convergence_tol=0.3, reg_epsilon=1e-3, max_it=100):
+    def solve(self, rho0, rhoT, r=1.0, convergence_tol=0.3, reg_epsilon=1e-3, max_it=100, poisson="dct_exact"):
         """rho0, rhoT: float64 CUDA tensors of P values, identical on every rank.
         Returns (u, v, m, info) as CUDA tensors on rank 0 (None elsewhere; info everywhere)."""
         torch, dist, ctx = self.torch, self.dist, self.ctx
@@ -140,15 +189,23 @@ class SlabSolver:
             w2 = (self.n0 + j) / (Nt - 1)
             self.mu[0, 1 + j] = (1 - w2) * rho0 + w2 * rhoT
         mu0, q0 = self.mu[0, 1].data_ptr(), self.q[0, 1].data_ptr()
-        crit, trace = -1.0, []
+        if poisson not in ("dct_exact", "cg_parity"):
+            raise ValueError(f"unknown Poisson back-end {poisson!r}")
+        crit, trace, cg_iters = -1.0, [], []
         for it in range(int(max_it)):
             self._halo([self.mu[0], self.q[0]])
             ctx.slab_rhs(mu0, q0, self.cs, rho0.data_ptr(), rhoT.data_ptr(), r, Nt, self.n0, L, Nx, Ny, self.F.data_ptr())
-            ctx.dct_xy(self.F.data_ptr(), self.A.data_ptr(), self.tmp.data_ptr(), L, Nt, Ny, Nx, False)
-            self._to_y_slabs(self.A, self.B)
-            ctx.dct_t_solve(self.B.data_ptr(), self.B2.data_ptr(), Nt, Ny, Nx, self.y0, self.nyl, r, reg_epsilon)
-            self._to_t_slabs(self.B2, self.A)
-            ctx.dct_xy(self.A.data_ptr(), self.phi[1].data_ptr(), self.tmp.data_ptr(), L, Nt, Ny, Nx, True)
+            if poisson == "cg_parity":
+                n_cg, cg_info = self._poisson_cg(r, reg_epsilon)
+                cg_iters.append(n_cg)
+                if cg_info > 0 and self.rank == 0:
+                    print(f"WARNING: CG did not converge in {cg_info} iterations.")      # benamou_brenier.py:86-87
+            else:
+                ctx.dct_xy(self.F.data_ptr(), self.A.data_ptr(), self.tmp.data_ptr(), L, Nt, Ny, Nx, False)
+                self._to_y_slabs(self.A, self.B)
+                ctx.dct_t_solve(self.B.data_ptr(), self.B2.data_ptr(), Nt, Ny, Nx, self.y0, self.nyl, r, reg_epsilon)
+                self._to_t_slabs(self.B2, self.A)
+                ctx.dct_xy(self.A.data_ptr(), self.phi[1].data_ptr(), self.tmp.data_ptr(), L, Nt, Ny, Nx, True)
             self._halo([self.phi])
             ctx.slab_prox(self.phi[1].data_ptr(), mu0, q0, self.cs, r, Nt, self.n0, L, Nx, Ny, self.sums.data_ptr())
             sums = self.sums
@@ -162,7 +219,7 @@ class SlabSolver:
                 break
             if prev >= 0 and abs(prev - crit) < 1e-5:
                 break
-        info = dict(n_outer=len(trace), crit=np.array(trace))
+        info = dict(n_outer=len(trace), crit=np.array(trace), cg_iters=np.array(cg_iters, dtype=np.int32))
         # trajectories need every plane of phi at arbitrary (x, y): gather the owned planes on rank 0
         own = self.phi[1:L + 1].contiguous()
         if self.world > 1:

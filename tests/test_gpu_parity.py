@@ -583,6 +583,25 @@ def test_slab_ranks_share_one_gpu_bit_identical(ranks, h, w, Nt):
     assert res["bit_identical"] and res["outer"] == res["single_gpu_outer"] and res["ranks"] == ranks
 
 
+@pytest.mark.parametrize("ranks,h,w,Nt", [(1, 48, 64, 5), (2, 48, 64, 5), (3, 61, 83, 7)])
+def test_slab_cg_parity_matches_single_gpu(ranks, h, w, Nt):
+    """The reference's truncated CG as the slab Poisson back-end (foto_slab_cg_dev: stepwise kernels, one boundary plane of r
+    and two all-reduces per CG iteration) against the one-GPU streaming kernel: same outer count, CG counts equal (or +-1 in
+    the rare flipped solve) and the flow to 1e-9 (5e-6 with a flip).  Ranks share GPU 0 over gloo, so it runs anywhere."""
+    import json
+    import subprocess
+    from conftest import ROOT
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ranks}", "--master-addr", "127.0.0.1",
+           "--master-port", "29535", os.path.join(ROOT, "tools", "run_slab.py"), str(h), str(w), str(Nt), "4", "--check", "--one-gpu", "--cg"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["outer"] == res["single_gpu_outer"] and res["ranks"] == ranks
+    a, b = np.array(res["cg_iters"]), np.array(res["single_gpu_cg_iters"])
+    assert np.all(np.abs(a - b) <= 1), (a, b)
+    assert res["max_rel_diff"] < (1e-9 if np.array_equal(a, b) else 5e-6), res
+
+
 def test_gn_large_image_streaming_property(cg_variant):
     """720x1280 does not fit the on-chip GN kernel: the spectral solver (auto) and the streaming Jacobi-PCG (forced)
     must return a solution of A x = b (residual checked with the library's own K5/K6 operator, which the goldens
