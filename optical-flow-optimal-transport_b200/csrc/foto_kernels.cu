@@ -50,49 +50,50 @@ __device__ __forceinline__ double wv(const double *__restrict__ mu, const double
     return mu[k] - r * q[k];
 }
 
-// One thread per (y, x) column marching through t: w_t = (mu - r q)_rho of the planes n-1, n, n+1 stays in registers, so every
-// word of mu and q is read once from HBM even when a plane (16 MB at 1080x1920) is far larger than what L2 keeps between two
-// visits.  Mapping the 256 threads of a block to an 8 x 32 or 4 x 64 tile of the plane (rows y-1, y+1 from L1 instead of L2: 70 -> 61 bytes
-// per cell from L2) was measured: 0.72-0.73 of the HBM peak against 0.75 for the plain run of 256 cells below (same box).
+__device__ __forceinline__ double dw_acc(double s, const double *__restrict__ mu, const double *__restrict__ q,
+                                         double r, unsigned int k, unsigned int st, int i, int n)
+{
+    if (i == 0) { s += -1.0 * wv(mu, q, r, k); s += 1.0 * wv(mu, q, r, k + st); }
+    else if (i == n - 1) { s += -1.0 * wv(mu, q, r, k - st); s += 1.0 * wv(mu, q, r, k); }
+    else { s += -0.5 * wv(mu, q, r, k - st); s += 0.5 * wv(mu, q, r, k + st); }
+    return s;
+}
+
+// Measured and rejected (same-box A/B at 1080x1920x16, this kernel: 0.772 of the HBM peak): the 256 threads of a block as an
+// 8 x 32 or 4 x 64 tile (rows y-1, y+1 from L1 instead of L2) 0.72-0.74; stencil points and weights as per-column constants with
+// two planes per trip 0.753, one 0.63, four 0.62.  A grid-stride kernel that only reads six streams and writes one reaches 1.03 of
+// the copy peak (tools/ubench_streams.cu), so the remaining gap is this kernel's halo re-reads through L2 (70 B per cell from L2).
+// One thread per (y, x) column marching through t: w_t = (mu - r q)_rho of the planes n-1, n, n+1
+// stays in registers, so every word of mu and q is read once from HBM even when a plane (16 MB at
+// 1080x1920) is far larger than what L2 keeps between two visits.
 __global__ void __launch_bounds__(kThreads, 8) k_rhs(Dims d, const double *__restrict__ mu, const double *__restrict__ q,
                                                    const double *__restrict__ rho0, const double *__restrict__ rhoT,
                                                    double r, double *__restrict__ F)
 {
     if (d.skip && *d.skip) return;
+    const unsigned int stride = gridDim.x * blockDim.x;
     const double *mu1 = mu + d.cs, *q1 = q + d.cs, *mu2 = mu + 2u * d.cs, *q2 = q + 2u * d.cs;
     auto has = [&](int nl) { const int gn = d.n0 + nl; return gn >= 0 && gn < d.gNt; };   // plane exists globally
-    auto column = [&](unsigned int i, int y, int x) {
-        // the two stencil points and weights of the x and y differences of this column (grad_1d_central_weird, operators.py:33-48:
-        // one-sided and unscaled on the first and last row, (-1/2, +1/2) inside); the products are the reference's
-        const long long xa = x == 0 ? 0 : -1, xb = x == d.Nx - 1 ? 0 : 1, ya = y == 0 ? 0 : -(long long)d.Nx, yb = y == d.Ny - 1 ? 0 : (long long)d.Nx;
-        const double cxa = (x == 0 || x == d.Nx - 1) ? -1.0 : -0.5, cxb = (x == 0 || x == d.Nx - 1) ? 1.0 : 0.5;
-        const double cya = (y == 0 || y == d.Ny - 1) ? -1.0 : -0.5, cyb = (y == 0 || y == d.Ny - 1) ? 1.0 : 0.5;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.P; i += stride) {
+        const int y = (int)(i / (unsigned int)d.Nx), x = (int)(i - (unsigned int)y * d.Nx);
         double w_m = has(-1) ? mu[(long long)i - (long long)d.P] - r * q[(long long)i - (long long)d.P] : 0.0;
         double w_c = wv(mu, q, r, i), w_p = has(1) ? wv(mu, q, r, d.P + i) : 0.0;
-        // two planes per trip: the loads of the second are in flight while the first is summed (0.75 of the HBM peak at
-        // 1080x1920x16 against 0.63 without and 0.62 with four, same box)
-#pragma unroll 2
         for (int n = 0; n < d.Nt; n++) {
-            const long long k = (long long)n * d.P + i;
+            const unsigned int k = (unsigned int)n * d.P + i;
             const int gn = d.n0 + n;
-            const double w1a = mu1[k + xa] - r * q1[k + xa], w1b = mu1[k + xb] - r * q1[k + xb];
-            const double w2a = mu2[k + ya] - r * q2[k + ya], w2b = mu2[k + yb] - r * q2[k + yb];
             double s = 0.0;
             if (gn == 0) { s += -1.0 * w_c; s += 1.0 * w_p; }
             else if (gn == d.gNt - 1) { s += -1.0 * w_m; s += 1.0 * w_c; }
             else { s += -0.5 * w_m; s += 0.5 * w_p; }
-            s += cxa * w1a; s += cxb * w1b;
-            s += cya * w2a; s += cyb * w2b;
+            s = dw_acc(s, mu1, q1, r, k, 1u, x, d.Nx);
+            s = dw_acc(s, mu2, q2, r, k, (unsigned int)d.Nx, y, d.Ny);
             if (gn == 0) s -= (rho0[i] - mu[k] + r * q[k]);
             if (gn == d.gNt - 1) s += (rhoT[i] - mu[k] + r * q[k]);
             F[k] = s;
             w_m = w_c; w_c = w_p;
-            if (n + 2 <= d.Nt && has(n + 2)) w_p = wv(mu, q, r, (unsigned int)k + 2u * d.P);   // local planes -1 .. Nt only
+            if (n + 2 <= d.Nt && has(n + 2)) w_p = wv(mu, q, r, k + 2u * d.P);   // local planes -1 .. Nt only
         }
-    };
-    const unsigned int stride = gridDim.x * blockDim.x;
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.P; i += stride)
-        column(i, (int)(i / (unsigned int)d.Nx), (int)(i % (unsigned int)d.Nx));
+    }
 }
 
 // --------------------------------------------------------------------------- stepB (project_K: prox_math.cuh)
