@@ -153,11 +153,11 @@ int  foto_dct_t_solve_dev(foto_ctx *ctx, const double *d_in, double *d_out, int 
 /* Time-slab form of the reference's truncated CG (benamou_brenier.py:85), one step per call; the caller issues the
  * collectives between the steps on the same stream (foto_b200/slab.py):
  *   op 0 init (x = 0, r = b, p = 0; partial b.b -> state[0])      then all-reduce state[0]
- *   op 1 after that all-reduce (atol, "done" if b = 0)
- *   per iteration it:  op 2 stop test + beta;  exchange the boundary planes of r;  op 3 phase A (p_new = p_old beta + r incl. the
- *   halo planes, q = A p_new, partial p.q -> state[0]);  all-reduce state[0];  op 4 alpha;  op 5 phase B (x, r update, partial
- *   r.r -> state[0]);  all-reduce state[0];  op 6
+ *   per iteration it:  exchange the boundary planes of r;  op 3 phase A (stop test and beta from state[0]; p_new = p_old beta + r
+ *   incl. the halo planes, q = A p_new, partial p.q -> state[0]);  all-reduce state[0];  op 5 phase B (alpha, x and r update,
+ *   partial r.r -> state[0]);  all-reduce state[0]
  *   op 7 after maxiter iterations without convergence.
+ * Kernels return at once when the state's done flag is up, so iterations may be enqueued ahead of the flag being read.
  * d_r, d_p_old, d_p_new point to plane 0 of [nloc + 2][Ny*Nx] arrays (planes -1 and nloc are halos); d_x, d_q, d_b: [nloc][Ny*Nx];
  * d_state: foto_slab_cg_state_words() doubles, zeroed before op 0: [4] done, [5] iterations, [6] info (scipy's). */
 int  foto_slab_cg_dev(foto_ctx *ctx, int op, int gNt, int n0, int nloc, int Ny, int Nx, double r, double eps, double rtol, int it,

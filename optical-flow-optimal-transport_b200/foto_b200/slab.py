@@ -160,15 +160,14 @@ class SlabSolver:
                 else:
                     dist.all_reduce(state[:1])
 
-        step(0); allreduce(); step(1)
+        step(0); allreduce()
         it = 0
         while it < maxiter:
             for _ in range(min(look, maxiter - it)):
                 pold, pnew = c["p"][it & 1], c["p"][(it + 1) & 1]
-                step(2, it, pold, pnew)
                 self._halo([rr])
-                step(3, it, pold, pnew); allreduce(); step(4, it, pold, pnew)
-                step(5, it, pold, pnew); allreduce(); step(6, it, pold, pnew)
+                step(3, it, pold, pnew); allreduce()          # stop test, p update incl. halo planes, q = A p, p.q
+                step(5, it, pold, pnew); allreduce()          # x, r update, r.r
                 it += 1
             if float(state[4]) != 0.0:
                 break
