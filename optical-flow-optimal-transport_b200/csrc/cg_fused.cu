@@ -421,7 +421,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) cg_fused_kernel(CgArgs a, Geom g)
                 if (cta == 0) root2(Placement{arp[0], arp[1], arp[2], arp[10]}, gen, ncta, tid);
             }
         }
-        export_edges((unsigned int)it);
+        export_edges((unsigned int)it);                  // first: the neighbours' imports wait for these words (x update first: 4.92
+                                                         // against 4.69 us; the root CTA taking the totals from its own root warp
+                                                         // instead of polling them: 4.75, same-box A/B)
         if (pend) { x_update(alpha_prev); pend = false; }
         double hv[kHaloPerThread] = {0.0, 0.0, 0.0, 0.0};
         auto import_edges = [&]() {
