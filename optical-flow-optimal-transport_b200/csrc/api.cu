@@ -493,7 +493,7 @@ static int gn_solve_spectral(foto_ctx *c, const double *d_f1, const double *d_f2
         CUDA_TRY(cudaMalloc((void **)&c->gn_state, 256));
         CUDA_TRY(cudaMallocHost((void **)&c->h_gn_state, kLookSlots * 256));
     }
-    const size_t n32 = ((size_t)3 * c->gn_tb.hp * c->gn_tb.wp + 1) / 2;     // one padded fp32 volume, in doubles
+    const size_t n32 = (c->gn_tb.volume_floats() + 1) / 2;                  // one padded fp32 volume, in doubles
     FOTO_TRY(ensure(&c->ws, &c->ws_bytes, 2 * Carver::bytes(P) + 7 * Carver::bytes(3 * P) + Carver::bytes(8) + Carver::bytes(6 * 1184) +
                                               Carver::bytes(3 * 592) + 4 * Carver::bytes(n32)));
     Carver cv(c->ws);

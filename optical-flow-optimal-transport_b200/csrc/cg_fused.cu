@@ -129,7 +129,7 @@ __device__ Placement place_allreduce(unsigned long long *base, unsigned int seq,
             st_relaxed_u64(rec + 1, choice);
             st_relaxed_u64(rec + 2, (unsigned long long)smid + 1);
         }
-        if (force & 0x80000000u) choice = (force & 0xFFFFFFu) | (choice & 0xFF000000ull);
+        if (force & 0x80000000u) choice = (force & 0xFFFFFFu) | ((unsigned long long)(force & 0xFF0000u) << 8);   // forced: one copy of the totals
         if (force & 0x20000000u) choice = (choice & 0xFFFFFFull) | ((choice & 0xFF0000ull) << 8);      // one copy of the totals only
         choice = (choice & 0xFFFFFFFFull) | ((unsigned long long)seq << 32);
         st_relaxed_u64(rec, choice);

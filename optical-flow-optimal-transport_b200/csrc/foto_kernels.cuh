@@ -153,6 +153,16 @@ int launch_gn_pcg(cudaStream_t st, const GnArgs &a, int grid, int block);
 struct GnDctTables {            // fp32 zero-padded DCT matrices, owned by the context, valid for (w, h)
     int w = 0, h = 0, wp = 0, hp = 0;
     float *base = nullptr, *Cx = nullptr, *CxT = nullptr, *Cy = nullptr, *CyT = nullptr;
+    // even / odd folded transforms (w and h even): half sizes padded to multiples of 4 and the folded matrices
+    // Ex[b][j][i] = Cx[2j+b][i] (i, j < w/2), ExT its transposes, the same for y
+    bool fold = false;
+    int wq = 0, hq = 0;
+    float *Ex = nullptr, *ExT = nullptr, *Ey = nullptr, *EyT = nullptr;
+    size_t volume_floats() const            // one fp32 work volume: natural [3][hp][wp] or folded [3][2 hq][2 wq] layouts
+    {
+        const size_t rows = fold && 2 * hq > hp ? 2 * hq : hp, cols = fold && 2 * wq > wp ? 2 * wq : wp;
+        return 3 * rows * cols;
+    }
 };
 struct GnDctArgs {
     const double *fx, *fy, *f2, *b;         // P, P, P, 3P
@@ -160,7 +170,7 @@ struct GnDctArgs {
     const GnDctTables *tb;
     double *x, *r, *p, *s, *wv;             // 3P each
     double *gbar, *partials6, *partials3;   // 8, 6 * 1184, 3 * 592
-    float *r32, *t1, *t2, *u32;             // 3 * hp * wp each
+    float *r32, *t1, *t2, *u32;             // tb->volume_floats() each
     void *state;                            // gn_dct_state_bytes()
     int w, h, maxiter;
     double alpha, lam, rtol;

@@ -61,7 +61,8 @@ template <int BM, int BN, int WM, int WN, int STAGES>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) k_sgemm_tf32(int M, int N, int K, const float *__restrict__ A, int lda,
                                                                           long long strideA, const float *__restrict__ B, int ldb,
                                                                           long long strideB, float *__restrict__ C, int ldc,
-                                                                          long long strideC, const int *skip)
+                                                                          long long strideC, const int *skip, int nb0, long long sA0,
+                                                                          long long sB0, long long sC0)
 {
     constexpr int GT = (BM / WM) * (BN / WN) * 32, BPITCH = BN + 8;      // B fragment loads hit bank 8t + g: conflict free
     constexpr int MI = WM / 16, NJ = WN / 8;
@@ -69,7 +70,10 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) k_sgemm_tf32(int M
     float (*As)[BM][APITCH] = reinterpret_cast<float (*)[BM][APITCH]>(gsm);                           // As[stage][m][k]
     float (*Bs)[BK][BPITCH] = reinterpret_cast<float (*)[BK][BPITCH]>(gsm + STAGES * BM * APITCH);    // Bs[stage][k][n]
     if (skip && *skip) return;
-    A += (size_t)blockIdx.z * strideA; B += (size_t)blockIdx.z * strideB; C += (size_t)blockIdx.z * strideC;
+    {   // two-level batch: blockIdx.z = z1 * nb0 + z0; offsets z0 * s?0 + z1 * stride?
+        const int z0 = (int)blockIdx.z % nb0, z1 = (int)blockIdx.z / nb0;
+        A += z0 * sA0 + z1 * strideA; B += z0 * sB0 + z1 * strideB; C += z0 * sC0 + z1 * strideC;
+    }
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp / (BN / WN)) * WM, wn = (warp % (BN / WN)) * WN;
@@ -153,10 +157,11 @@ struct GemmCfg {
     static constexpr int smem = STAGES * (BM * APITCH + BK * (BN + 8)) * (int)sizeof(float);
     static constexpr int threads = (BM / WM) * (BN / WN) * 32;
     static void launch(cudaStream_t st, int M, int N, int K, const float *A, int lda, long long sA, const float *B, int ldb, long long sB,
-                       float *C, int ldc, long long sC, int batch, const int *skip)
+                       float *C, int ldc, long long sC, int batch, const int *skip, int nb0 = 1, long long sA0 = 0, long long sB0 = 0,
+                       long long sC0 = 0)
     {
-        dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch);
-        k_sgemm_tf32<BM, BN, WM, WN, STAGES><<<grid, threads, smem, st>>>(M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, skip);
+        dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch * nb0);
+        k_sgemm_tf32<BM, BN, WM, WN, STAGES><<<grid, threads, smem, st>>>(M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, skip, nb0, sA0, sB0, sC0);
     }
     static cudaError_t prepare() { return cudaFuncSetAttribute(k_sgemm_tf32<BM, BN, WM, WN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
 };
@@ -243,6 +248,109 @@ __global__ void __launch_bounds__(256) k_spectral(int w, int h, int wp, int hp, 
     const size_t i0 = ((size_t)a) * wp + b, cs = (size_t)hp * wp;
     const double r0 = T[i0], r1 = T[cs + i0], r2 = T[2 * cs + i0];
     // adjugate of the symmetric 3 x 3 matrix
+    const double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
+    const double c11 = m00 * m22 - m02 * m02, c12 = m01 * m02 - m00 * m12, c22 = m00 * m11 - m01 * m01;
+    const double det = m00 * c00 + m01 * c01 + m02 * c02;
+    const double id = det != 0.0 ? 1.0 / det : 0.0;
+    T[i0] = (float)((c00 * r0 + c01 * r1 + c02 * r2) * id);
+    T[cs + i0] = (float)((c01 * r0 + c11 * r1 + c12 * r2) * id);
+    T[2 * cs + i0] = (float)((c02 * r0 + c12 * r1 + c22 * r2) * id);
+}
+
+// ---- even / odd folded transforms (w and h even): the DCT-II matrix satisfies C[k][n-1-i] = (-1)^k C[k][i], so a transform of
+// length n is two transforms of length n/2 on the sums and differences x[i] +- x[n-1-i] (dct_kernels.cu, k_fold): half the
+// flops and half the L2 traffic of the GEMMs, which is what they are bound by here.  The spectrum lives in the order
+// "even frequencies, then odd" along both axes, in a [3][2 hq][2 wq] layout (hq, wq = half sizes padded to multiples of 4).
+
+// fp64 n x n DCT matrix -> fp32 q x q: out[j][i] = C[2j+b][i] (transpose: out[i][j]) for i, j < n/2, zero padded
+__global__ void k_pad_folded(int n, int q, int b, int transpose, const double *__restrict__ in, float *__restrict__ out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= q * q) return;
+    const int r = k / q, c = k - r * q, j = transpose ? c : r, i = transpose ? r : c;
+    out[k] = (j < n / 2 && i < n / 2) ? (float)in[(size_t)(2 * j + b) * n + i] : 0.f;
+}
+
+// fold the middle axis of in[outer][n][inner] (outer stride so_in, row stride = inner_ld): out[b][outer][q][inner_ld] with
+// rows >= n/2 zeroed (b = 0 sums, 1 differences; out outer stride = q * inner_ld, b stride = bs)
+__global__ void __launch_bounds__(256) k_fold32(int outer, int n, int q, int inner, int inner_ld, long long so_in, const float *__restrict__ in,
+                                                 float *__restrict__ out, long long bs, const int *skip)
+{
+    if (skip && *skip) return;
+    const long long total = (long long)outer * q * inner_ld;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k % inner_ld);
+        const long long oj = k / inner_ld;
+        const int j = (int)(oj % q), o = (int)(oj / q);
+        float e = 0.f, d = 0.f;
+        if (j < n / 2 && i < inner) {
+            const float a = in[o * so_in + (long long)j * inner_ld + i], c = in[o * so_in + (long long)(n - 1 - j) * inner_ld + i];
+            e = a + c; d = a - c;
+        }
+        out[k] = e; out[bs + k] = d;
+    }
+}
+// inverse: out[outer][j][i] = E + O, out[outer][n-1-j][i] = E - O for j < n/2
+__global__ void __launch_bounds__(256) k_unfold32(int outer, int n, int q, int inner, int inner_ld, long long so_out, const float *__restrict__ in,
+                                                   long long bs, float *__restrict__ out, const int *skip)
+{
+    if (skip && *skip) return;
+    const long long total = (long long)outer * (n / 2) * inner;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k % inner);
+        const long long oj = k / inner;
+        const int j = (int)(oj % (n / 2)), o = (int)(oj / (n / 2));
+        const long long src = ((long long)o * q + j) * inner_ld + i;
+        const float e = in[src], d = in[bs + src];
+        out[o * so_out + (long long)j * inner_ld + i] = e + d;
+        out[o * so_out + (long long)(n - 1 - j) * inner_ld + i] = e - d;
+    }
+}
+// the x axis is the innermost one: fold / unfold with the partner n-1-i inside a row.  in: rows x ld_in; folded: [b][rows][q]
+__global__ void __launch_bounds__(256) k_fold32_x(int rows, int n, int q, int ld_in, const float *__restrict__ in, float *__restrict__ out,
+                                                   const int *skip)
+{
+    if (skip && *skip) return;
+    const long long total = (long long)rows * q, bs = total;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k % q);
+        const long long r = k / q;
+        float e = 0.f, d = 0.f;
+        if (i < n / 2) { const float a = in[r * ld_in + i], c = in[r * ld_in + (n - 1 - i)]; e = a + c; d = a - c; }
+        out[k] = e; out[bs + k] = d;
+    }
+}
+__global__ void __launch_bounds__(256) k_unfold32_x(int rows, int n, int q, int ld_out, const float *__restrict__ in, float *__restrict__ out,
+                                                     const int *skip)
+{
+    if (skip && *skip) return;
+    const long long total = (long long)rows * (n / 2), bs = (long long)rows * q;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k % (n / 2));
+        const long long r = k / (n / 2);
+        const float e = in[r * q + i], d = in[bs + r * q + i];
+        out[r * ld_out + i] = e + d;
+        out[r * ld_out + (n - 1 - i)] = e - d;
+    }
+}
+
+// k_spectral on the folded layout T[3][2 hq][2 wq]: position (by hq + jy, bx wq + jx) holds frequency (2 jy + by, 2 jx + bx)
+__global__ void __launch_bounds__(256) k_spectral_folded(int w, int h, int wq, int hq, double alpha, double lam, const double *__restrict__ lam_x,
+                                                          const double *__restrict__ lam_y, const double *__restrict__ gbar, float *__restrict__ T,
+                                                          const int *skip)
+{
+    if (skip && *skip) return;
+    const unsigned int P = (unsigned int)w * h, k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P) return;
+    const int hx = w / 2, hy = h / 2;
+    const int ra = (int)(k / (unsigned int)w), rb = (int)(k - (unsigned int)ra * w);       // enumerate valid positions
+    const int by = ra / hy, jy = ra - by * hy, bx = rb / hx, jx = rb - bx * hx;
+    const double mu = lam_y[2 * jy + by] + lam_x[2 * jx + bx];
+    const double reg = 1e-6 * (gbar[0] + gbar[3] + gbar[5]) + 1e-300;
+    const double m00 = alpha * mu + gbar[0] + reg, m01 = gbar[1], m02 = gbar[2], m11 = alpha * mu + gbar[3] + reg, m12 = gbar[4],
+                 m22 = lam * mu + gbar[5] + reg;
+    const size_t i0 = ((size_t)(by * hq + jy)) * (2 * wq) + (bx * wq + jx), cs = (size_t)(2 * hq) * (2 * wq);
+    const double r0 = T[i0], r1 = T[cs + i0], r2 = T[2 * cs + i0];
     const double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
     const double c11 = m00 * m22 - m02 * m02, c12 = m01 * m02 - m00 * m12, c22 = m00 * m11 - m01 * m01;
     const double det = m00 * c00 + m01 * c01 + m02 * c02;
@@ -367,13 +475,14 @@ int tile_mode(int, int)
     if (forced == -2) { const char *e = getenv("FOTO_GN_TILE"); forced = e ? atoi(e) : -1; }
     return forced >= 0 ? forced : 0;
 }
+// batch index = z1 * nb0 + z0 with offsets z1 * s? + z0 * s?0
 void gemm(cudaStream_t st, int M, int N, int K, const float *A, int lda, long long sA, const float *B, int ldb, long long sB,
-          float *C, int ldc, long long sC, int batch, const int *skip)
+          float *C, int ldc, long long sC, int batch, const int *skip, int nb0 = 1, long long sA0 = 0, long long sB0 = 0, long long sC0 = 0)
 {
     switch (tile_mode(M, N)) {
-    case 1: GemmWide::launch(st, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch, skip); break;
-    case 2: GemmTall::launch(st, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch, skip); break;
-    default: GemmSmall::launch(st, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch, skip); break;
+    case 1: GemmWide::launch(st, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch, skip, nb0, sA0, sB0, sC0); break;
+    case 2: GemmTall::launch(st, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch, skip, nb0, sA0, sB0, sC0); break;
+    default: GemmSmall::launch(st, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch, skip, nb0, sA0, sB0, sC0); break;
     }
 }
 
@@ -381,22 +490,37 @@ void gemm(cudaStream_t st, int M, int N, int K, const float *A, int lda, long lo
 
 size_t gn_dct_state_bytes() { return sizeof(GnDctState); }
 
-// fp32 zero-padded copies of the DCT matrices of DctTables (Cx, CxT: wp x wp; Cy, CyT: hp x hp)
+// fp32 zero-padded copies of the DCT matrices of DctTables (Cx, CxT: wp x wp; Cy, CyT: hp x hp) and, for even w and h, the
+// folded matrices (used from 1 M pixels on).
 int gn_dct_prepare_tables(cudaStream_t st, const DctTables &tb, int w, int h, GnDctTables &out)
 {
     const int wp = (w + 3) & ~3, hp = (h + 3) & ~3;
-    if (out.base && out.w == w && out.h == h) return FOTO_OK;
+    // measured (ms per solve, folded / dense): 388x584 9.0 / 8.5, 380x420 7.4 / 6.4, 480x640 10.6 / 10.1, 1080x1920 58 / 81: below ~1 M
+    // pixels the four extra launches of an application cost more than the halved GEMMs save (they are launch bound there)
+    const char *env = getenv("FOTO_GN_FOLD");           // 0 / 1: force (A/B)
+    const bool fold = !(w & 1) && !(h & 1) && (env ? atoi(env) != 0 : (long long)w * h >= (1ll << 20));
+    if (out.base && out.w == w && out.h == h && out.fold == fold) return FOTO_OK;
     if (out.base) { CUDA_TRY(cudaFree(out.base)); out = GnDctTables(); }
-    const size_t nx = (size_t)wp * wp, ny = (size_t)hp * hp;
-    CUDA_TRY(cudaMalloc((void **)&out.base, (2 * nx + 2 * ny) * sizeof(float)));
+    const int wq = (w / 2 + 3) & ~3, hq = (h / 2 + 3) & ~3;
+    const size_t nx = (size_t)wp * wp, ny = (size_t)hp * hp, qx = (size_t)wq * wq, qy = (size_t)hq * hq;
+    CUDA_TRY(cudaMalloc((void **)&out.base, (2 * nx + 2 * ny + (fold ? 4 * qx + 4 * qy : 0)) * sizeof(float)));
     out.Cx = out.base; out.CxT = out.Cx + nx; out.Cy = out.CxT + nx; out.CyT = out.Cy + ny;
     k_pad_matrix<<<(unsigned int)((nx + 255) / 256), 256, 0, st>>>(w, wp, tb.Cx, out.Cx);
     k_pad_matrix<<<(unsigned int)((nx + 255) / 256), 256, 0, st>>>(w, wp, tb.CxT, out.CxT);
     k_pad_matrix<<<(unsigned int)((ny + 255) / 256), 256, 0, st>>>(h, hp, tb.Cy, out.Cy);
     k_pad_matrix<<<(unsigned int)((ny + 255) / 256), 256, 0, st>>>(h, hp, tb.CyT, out.CyT);
+    if (fold) {
+        out.Ex = out.CyT + ny; out.ExT = out.Ex + 2 * qx; out.Ey = out.ExT + 2 * qx; out.EyT = out.Ey + 2 * qy;
+        for (int b = 0; b < 2; b++) {
+            k_pad_folded<<<(unsigned int)((qx + 255) / 256), 256, 0, st>>>(w, wq, b, 0, tb.Cx, out.Ex + b * qx);
+            k_pad_folded<<<(unsigned int)((qx + 255) / 256), 256, 0, st>>>(w, wq, b, 1, tb.Cx, out.ExT + b * qx);
+            k_pad_folded<<<(unsigned int)((qy + 255) / 256), 256, 0, st>>>(h, hq, b, 0, tb.Cy, out.Ey + b * qy);
+            k_pad_folded<<<(unsigned int)((qy + 255) / 256), 256, 0, st>>>(h, hq, b, 1, tb.Cy, out.EyT + b * qy);
+        }
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(GemmSmall::prepare()); CUDA_TRY(GemmWide::prepare()); CUDA_TRY(GemmTall::prepare());       // per device: tables are per context
-    out.w = w; out.h = h; out.wp = wp; out.hp = hp;
+    out.w = w; out.h = h; out.wp = wp; out.hp = hp; out.fold = fold; out.wq = wq; out.hq = hq;
     return FOTO_OK;
 }
 
@@ -407,7 +531,8 @@ int gn_dct_begin(cudaStream_t st, const GnDctArgs &a)
     const int blocks = (int)((P + 255) / 256) < 1184 ? (int)((P + 255) / 256) : 1184;
     k_gbar_partial<<<blocks, 256, 0, st>>>(P, a.fx, a.fy, a.f2, a.partials6);
     k_gbar_final<<<1, 256, 0, st>>>(a.partials6, blocks, 1.0 / (double)P, a.gbar, (GnDctState *)a.state);
-    CUDA_TRY(cudaMemsetAsync(a.r32, 0, (size_t)3 * a.tb->hp * a.tb->wp * sizeof(float), st));     // padding rows / columns stay zero
+    for (float *buf : {a.r32, a.t1, a.t2, a.u32})        // padding rows / columns stay zero
+        CUDA_TRY(cudaMemsetAsync(buf, 0, a.tb->volume_floats() * sizeof(float), st));
     k_init<<<(P + 255) / 256, 256, 0, st>>>(a.w, a.h, a.tb->wp, a.tb->hp, a.b, a.x, a.r, a.p, a.s, a.r32);
     CUDA_TRY(cudaGetLastError());
     return FOTO_OK;
@@ -422,6 +547,22 @@ int gn_dct_enqueue_iterations(cudaStream_t st, const GnDctArgs &a, int it0, int 
     const int *skip = &((GnDctState *)a.state)->done;
     const int pblocks = (int)((P + 255) / 256), nblk = pblocks < 592 ? pblocks : 592;
     for (int it = it0; it < it0 + count; it++) {
+        if (tb.fold) {
+            // u = M^-1 r with folded transforms: fold x, X GEMMs (sums | differences), fold y, Y GEMMs, 3x3 solve per frequency on
+            // the permuted spectrum [3][2 hq][2 wq], and back
+            const int wq = tb.wq, hq = tb.hq, wpp = 2 * wq, R = 3 * hp, fb = 148 * 8;
+            const long long qx = (long long)wq * wq, qy = (long long)hq * hq, fyb = (long long)3 * hq * wpp, cs2 = (long long)2 * hq * wpp;
+            k_fold32_x<<<fb, 256, 0, st>>>(R, w, wq, wp, a.r32, a.t1, skip);                                                     // t1 = FX[b][R][wq]
+            gemm(st, R, wq, wq, a.t1, wq, 0, tb.ExT, wq, 0, a.t2, wpp, 0, 1, skip, 2, (long long)R * wq, qx, wq);                // t2 = T1[R][wpp]
+            k_fold32<<<fb, 256, 0, st>>>(3, h, hq, wpp, wpp, (long long)hp * wpp, a.t2, a.t1, fyb, skip);                       // t1 = FY[b][3][hq][wpp]
+            gemm(st, hq, wpp, hq, tb.Ey, hq, 0, a.t1, wpp, (long long)hq * wpp, a.t2, wpp, cs2, 3, skip, 2, qy, fyb, (long long)hq * wpp);   // t2 = T2[3][2hq][wpp]
+            k_spectral_folded<<<pblocks, 256, 0, st>>>(w, h, wq, hq, a.alpha, a.lam, a.lam_x, a.lam_y, a.gbar, a.t2, skip);
+            gemm(st, hq, wpp, hq, tb.EyT, hq, 0, a.t2, wpp, cs2, a.t1, wpp, (long long)hq * wpp, 3, skip, 2, qy, (long long)hq * wpp, fyb); // t1 = GY[b][3][hq][wpp]
+            k_unfold32<<<fb, 256, 0, st>>>(3, h, hq, wpp, wpp, (long long)hp * wpp, a.t1, fyb, a.t2, skip);                      // t2 = T1'[3][hp][wpp]
+            gemm(st, R, wq, wq, a.t2, wpp, 0, tb.Ex, wq, 0, a.t1, wq, 0, 1, skip, 2, wq, qx, (long long)R * wq);                 // t1 = GX[b][R][wq]
+            k_unfold32_x<<<fb, 256, 0, st>>>(R, w, wq, wp, a.t1, a.u32, skip);
+            *launches += 4;
+        } else {
         // u = M^-1 r:  T1 = R32 * CxT (rows of all three components at once), T2_c = Cy * T1_c, 3x3 solve per frequency,
         // T1_c = CyT * T2_c, U = T1 * Cx
         gemm(st, 3 * hp, wp, wp, a.r32, wp, 0, tb.CxT, wp, 0, a.t1, wp, 0, 1, skip);
@@ -429,6 +570,7 @@ int gn_dct_enqueue_iterations(cudaStream_t st, const GnDctArgs &a, int it0, int 
         k_spectral<<<pblocks, 256, 0, st>>>(w, h, wp, hp, a.alpha, a.lam, a.lam_x, a.lam_y, a.gbar, a.t2, skip);
         gemm(st, hp, wp, hp, tb.CyT, hp, 0, a.t2, wp, cs, a.t1, wp, cs, 3, skip);
         gemm(st, 3 * hp, wp, wp, a.t1, wp, 0, tb.Cx, wp, 0, a.u32, wp, 0, 1, skip);
+        }
         k_stencil_dots<<<nblk, 256, 0, st>>>(w, h, wp, hp, a.alpha, a.lam, a.fx, a.fy, a.f2, a.u32, a.r, a.wv, a.partials3, skip);
         k_update<<<nblk, 256, 0, st>>>(w, h, wp, hp, a.partials3, nblk, it, a.maxiter, a.rtol, a.u32, a.wv, a.x, a.r, a.p, a.s, a.r32,
                                        (GnDctState *)a.state);

@@ -583,6 +583,25 @@ def test_slab_ranks_share_one_gpu_bit_identical(ranks, h, w, Nt):
     assert res["bit_identical"] and res["outer"] == res["single_gpu_outer"] and res["ranks"] == ranks
 
 
+def test_allreduce_placement_does_not_change_results(monkeypatch):
+    """The on-chip CG kernel keeps its all-reduce words in 2 KB granules it has classified by die (cg_fused.cu,
+    place_allreduce).  Where the words live must never change a bit of the answer: forced placements (FOTO_AR_PLACE), the
+    single-copy broadcast and the automatic choice give identical flows and CG counts."""
+    h, w, Nt = 97, 146, 4
+    f0, f1 = synth.make_pair(h, w, seed=5)
+    kw = dict(r=1.0, convergence_tol=0.1, reg_epsilon=1e-3, max_it=4)
+    ref = foto_b200.solve(f0, f1, Nt, w, h, **kw)
+    for env in ({"FOTO_AR_PLACE": "0,1,2"}, {"FOTO_AR_PLACE": "29,30,31"}, {"FOTO_AR_PLACE": "5,17,9", "FOTO_AR_ONECOPY": "1"}, {"FOTO_AR_ONECOPY": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        out = foto_b200.solve(f0, f1, Nt, w, h, **kw)
+        for k in env:
+            monkeypatch.delenv(k)
+        np.testing.assert_array_equal(out[3]["cg_iters"], ref[3]["cg_iters"])
+        for a, b in zip(out[:3], ref[:3]):
+            np.testing.assert_array_equal(a, b)
+
+
 @pytest.mark.parametrize("ranks,h,w,Nt", [(1, 48, 64, 5), (2, 48, 64, 5), (3, 61, 83, 7)])
 def test_slab_cg_parity_matches_single_gpu(ranks, h, w, Nt):
     """The reference's truncated CG as the slab Poisson back-end (foto_slab_cg_dev: stepwise kernels, one boundary plane of r
@@ -600,6 +619,22 @@ def test_slab_cg_parity_matches_single_gpu(ranks, h, w, Nt):
     a, b = np.array(res["cg_iters"]), np.array(res["single_gpu_cg_iters"])
     assert np.all(np.abs(a - b) <= 1), (a, b)
     assert res["max_rel_diff"] < (1e-9 if np.array_equal(a, b) else 5e-6), res
+
+
+@pytest.mark.parametrize("h,w", [(48, 64), (388, 584), (130, 210)])
+def test_gn_folded_preconditioner_equals_dense(h, w, monkeypatch):
+    """The spectral GN preconditioner with even / odd folded transforms (automatic from 1 M pixels on, forced here with
+    FOTO_GN_FOLD) against the dense transforms: same solution to 1e-11 and the same PCG iteration count (+-2); 130x210
+    exercises half sizes that need padding to multiples of 4."""
+    f0, f1 = synth.make_pair(h, w, seed=3 * h + w)
+    res = {}
+    for fold in ("0", "1"):
+        monkeypatch.setenv("FOTO_GN_FOLD", fold)
+        res[fold] = foto_b200.gn_solve(f0, f1, w, h, 0.1, 0.2)
+    monkeypatch.delenv("FOTO_GN_FOLD")
+    assert abs(res["0"][3]["iters"] - res["1"][3]["iters"]) <= 2 and res["1"][3]["info"] == 0
+    for a, b in zip(res["0"][:3], res["1"][:3]):
+        assert relerr(a, b) < 1e-11
 
 
 def test_gn_large_image_streaming_property(cg_variant):
