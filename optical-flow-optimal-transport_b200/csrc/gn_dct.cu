@@ -61,8 +61,7 @@ template <int BM, int BN, int WM, int WN, int STAGES>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) k_sgemm_tf32(int M, int N, int K, const float *__restrict__ A, int lda,
                                                                           long long strideA, const float *__restrict__ B, int ldb,
                                                                           long long strideB, float *__restrict__ C, int ldc,
-                                                                          long long strideC, const int *skip, int nb0, long long sA0,
-                                                                          long long sB0, long long sC0)
+                                                                          long long strideC, const int *skip)
 {
     constexpr int GT = (BM / WM) * (BN / WN) * 32, BPITCH = BN + 8;      // B fragment loads hit bank 8t + g: conflict free
     constexpr int MI = WM / 16, NJ = WN / 8;
@@ -70,10 +69,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32) k_sgemm_tf32(int M
     float (*As)[BM][APITCH] = reinterpret_cast<float (*)[BM][APITCH]>(gsm);                           // As[stage][m][k]
     float (*Bs)[BK][BPITCH] = reinterpret_cast<float (*)[BK][BPITCH]>(gsm + STAGES * BM * APITCH);    // Bs[stage][k][n]
     if (skip && *skip) return;
-    {   // two-level batch: blockIdx.z = z1 * nb0 + z0; offsets z0 * s?0 + z1 * stride?
-        const int z0 = (int)blockIdx.z % nb0, z1 = (int)blockIdx.z / nb0;
-        A += z0 * sA0 + z1 * strideA; B += z0 * sB0 + z1 * strideB; C += z0 * sC0 + z1 * strideC;
-    }
+    A += (size_t)blockIdx.z * strideA; B += (size_t)blockIdx.z * strideB; C += (size_t)blockIdx.z * strideC;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp / (BN / WN)) * WM, wn = (warp % (BN / WN)) * WN;
@@ -157,11 +153,10 @@ struct GemmCfg {
     static constexpr int smem = STAGES * (BM * APITCH + BK * (BN + 8)) * (int)sizeof(float);
     static constexpr int threads = (BM / WM) * (BN / WN) * 32;
     static void launch(cudaStream_t st, int M, int N, int K, const float *A, int lda, long long sA, const float *B, int ldb, long long sB,
-                       float *C, int ldc, long long sC, int batch, const int *skip, int nb0 = 1, long long sA0 = 0, long long sB0 = 0,
-                       long long sC0 = 0)
+                       float *C, int ldc, long long sC, int batch, const int *skip)
     {
-        dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch * nb0);
-        k_sgemm_tf32<BM, BN, WM, WN, STAGES><<<grid, threads, smem, st>>>(M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, skip, nb0, sA0, sB0, sC0);
+        dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch);
+        k_sgemm_tf32<BM, BN, WM, WN, STAGES><<<grid, threads, smem, st>>>(M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, skip);
     }
     static cudaError_t prepare() { return cudaFuncSetAttribute(k_sgemm_tf32<BM, BN, WM, WN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
 };
@@ -475,14 +470,13 @@ int tile_mode(int, int)
     if (forced == -2) { const char *e = getenv("FOTO_GN_TILE"); forced = e ? atoi(e) : -1; }
     return forced >= 0 ? forced : 0;
 }
-// batch index = z1 * nb0 + z0 with offsets z1 * s? + z0 * s?0
 void gemm(cudaStream_t st, int M, int N, int K, const float *A, int lda, long long sA, const float *B, int ldb, long long sB,
-          float *C, int ldc, long long sC, int batch, const int *skip, int nb0 = 1, long long sA0 = 0, long long sB0 = 0, long long sC0 = 0)
+          float *C, int ldc, long long sC, int batch, const int *skip)
 {
     switch (tile_mode(M, N)) {
-    case 1: GemmWide::launch(st, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch, skip, nb0, sA0, sB0, sC0); break;
-    case 2: GemmTall::launch(st, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch, skip, nb0, sA0, sB0, sC0); break;
-    default: GemmSmall::launch(st, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch, skip, nb0, sA0, sB0, sC0); break;
+    case 1: GemmWide::launch(st, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch, skip); break;
+    case 2: GemmTall::launch(st, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch, skip); break;
+    default: GemmSmall::launch(st, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch, skip); break;
     }
 }
 
@@ -553,15 +547,17 @@ int gn_dct_enqueue_iterations(cudaStream_t st, const GnDctArgs &a, int it0, int 
             const int wq = tb.wq, hq = tb.hq, wpp = 2 * wq, R = 3 * hp, fb = 148 * 8;
             const long long qx = (long long)wq * wq, qy = (long long)hq * hq, fyb = (long long)3 * hq * wpp, cs2 = (long long)2 * hq * wpp;
             k_fold32_x<<<fb, 256, 0, st>>>(R, w, wq, wp, a.r32, a.t1, skip);                                                     // t1 = FX[b][R][wq]
-            gemm(st, R, wq, wq, a.t1, wq, 0, tb.ExT, wq, 0, a.t2, wpp, 0, 1, skip, 2, (long long)R * wq, qx, wq);                // t2 = T1[R][wpp]
+            gemm(st, R, wq, wq, a.t1, wq, (long long)R * wq, tb.ExT, wq, qx, a.t2, wpp, wq, 2, skip);                           // t2 = T1[R][wpp]
             k_fold32<<<fb, 256, 0, st>>>(3, h, hq, wpp, wpp, (long long)hp * wpp, a.t2, a.t1, fyb, skip);                       // t1 = FY[b][3][hq][wpp]
-            gemm(st, hq, wpp, hq, tb.Ey, hq, 0, a.t1, wpp, (long long)hq * wpp, a.t2, wpp, cs2, 3, skip, 2, qy, fyb, (long long)hq * wpp);   // t2 = T2[3][2hq][wpp]
+            for (int b = 0; b < 2; b++)       // (a second batch level inside the kernel cost the dense path 9 %: 94 -> 72 registers)
+                gemm(st, hq, wpp, hq, tb.Ey + b * qy, hq, 0, a.t1 + b * fyb, wpp, (long long)hq * wpp, a.t2 + b * (long long)hq * wpp, wpp, cs2, 3, skip);   // t2 = T2[3][2hq][wpp]
             k_spectral_folded<<<pblocks, 256, 0, st>>>(w, h, wq, hq, a.alpha, a.lam, a.lam_x, a.lam_y, a.gbar, a.t2, skip);
-            gemm(st, hq, wpp, hq, tb.EyT, hq, 0, a.t2, wpp, cs2, a.t1, wpp, (long long)hq * wpp, 3, skip, 2, qy, (long long)hq * wpp, fyb); // t1 = GY[b][3][hq][wpp]
+            for (int b = 0; b < 2; b++)
+                gemm(st, hq, wpp, hq, tb.EyT + b * qy, hq, 0, a.t2 + b * (long long)hq * wpp, wpp, cs2, a.t1 + b * fyb, wpp, (long long)hq * wpp, 3, skip); // t1 = GY[b][3][hq][wpp]
             k_unfold32<<<fb, 256, 0, st>>>(3, h, hq, wpp, wpp, (long long)hp * wpp, a.t1, fyb, a.t2, skip);                      // t2 = T1'[3][hp][wpp]
-            gemm(st, R, wq, wq, a.t2, wpp, 0, tb.Ex, wq, 0, a.t1, wq, 0, 1, skip, 2, wq, qx, (long long)R * wq);                 // t1 = GX[b][R][wq]
+            gemm(st, R, wq, wq, a.t2, wpp, wq, tb.Ex, wq, qx, a.t1, wq, (long long)R * wq, 2, skip);                            // t1 = GX[b][R][wq]
             k_unfold32_x<<<fb, 256, 0, st>>>(R, w, wq, wp, a.t1, a.u32, skip);
-            *launches += 4;
+            *launches += 6;
         } else {
         // u = M^-1 r:  T1 = R32 * CxT (rows of all three components at once), T2_c = Cy * T1_c, 3x3 solve per frequency,
         // T1_c = CyT * T2_c, U = T1 * Cx
