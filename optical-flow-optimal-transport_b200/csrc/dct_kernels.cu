@@ -259,6 +259,66 @@ void dct_host_folded(int n, const std::vector<double> &C, const std::vector<doub
         }
 }
 
+// Second level (n a multiple of 8, q = n / 4): the even half is itself a DCT-II of length h = n / 2 on e1[i] = x[i] + x[n-1-i]
+// (C_n[2j][h-1-i] = (-1)^j C_n[2j][i]), so it folds once more: three transforms q x q, q x q, h x h = 3/8 of the dense flops, and
+// still one pass over the data each way.  Blocks of the folded array: [e2 | o2 | o1] of q, q and h rows of `inner` words per
+// outer index; spectrum order: frequencies 4m, then 4m+2, then 2j+1.
+__global__ void __launch_bounds__(256) k_fold2(size_t total, int n, int inner, const double *__restrict__ in, double *__restrict__ out,
+                                                size_t outer)
+{
+    const int h = n >> 1, q = n >> 2;
+    const size_t o2off = outer * q * inner, o1off = 2 * o2off;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = k % inner, oh = k / inner, o = oh / h;
+        const int j = (int)(oh % h);
+        const double a = in[(o * n + j) * inner + i], b = in[(o * n + (n - 1 - j)) * inner + i];
+        out[o1off + k] = a - b;
+        if (j < q) {
+            const double c = in[(o * n + (h - 1 - j)) * inner + i], d = in[(o * n + (h + j)) * inner + i];
+            const double e1a = a + b, e1b = c + d;
+            const size_t kk = (o * q + j) * inner + i;
+            out[kk] = e1a + e1b;
+            out[o2off + kk] = e1a - e1b;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_unfold2(size_t total, int n, int inner, const double *__restrict__ in, double *__restrict__ out,
+                                                  size_t outer)
+{
+    const int h = n >> 1, q = n >> 2;
+    const size_t o2off = outer * q * inner, o1off = 2 * o2off;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {   // total = outer q inner
+        const size_t i = k % inner, oq = k / inner, o = oq / q;
+        const int j = (int)(oq % q);
+        const double E2 = in[k], O2 = in[o2off + k];
+        const double E1a = E2 + O2, E1b = E2 - O2;                      // E1[j], E1[h-1-j]
+        const double O1a = in[o1off + (o * h + j) * inner + i], O1b = in[o1off + (o * h + (h - 1 - j)) * inner + i];
+        out[(o * n + j) * inner + i] = E1a + O1a;
+        out[(o * n + (n - 1 - j)) * inner + i] = E1a - O1a;
+        out[(o * n + (h - 1 - j)) * inner + i] = E1b + O1b;
+        out[(o * n + (h + j)) * inner + i] = E1b - O1b;
+    }
+}
+
+// Second-level tables of one axis (n a multiple of 8, q = n / 4): E2[c][m][i] = C[4m + 2c][i], i < q; E2T its transposes;
+// lam_p2 = (lam[4m] | lam[4m+2] | lam[2j+1])
+void dct_host_folded2(int n, const std::vector<double> &C, const std::vector<double> &lam, std::vector<double> &E2,
+                      std::vector<double> &E2T, std::vector<double> &lam_p2)
+{
+    const int h = n / 2, q = n / 4;
+    E2.assign((size_t)2 * q * q, 0.0); E2T.assign((size_t)2 * q * q, 0.0); lam_p2.assign(n, 0.0);
+    for (int c = 0; c < 2; c++)
+        for (int m = 0; m < q; m++) {
+            lam_p2[c * q + m] = lam[4 * m + 2 * c];
+            for (int i = 0; i < q; i++) {
+                const double v = C[(size_t)(4 * m + 2 * c) * n + i];
+                E2[((size_t)c * q + m) * q + i] = v;
+                E2T[((size_t)c * q + i) * q + m] = v;
+            }
+        }
+    for (int j = 0; j < h; j++) lam_p2[h + j] = lam[2 * j + 1];
+}
+
 template <int BM, int BN, int STAGES>
 struct DGemm {
     static constexpr int smem = STAGES * (BM * APITCH + BK * (BN + 4)) * (int)sizeof(double);
@@ -311,9 +371,9 @@ static int t_solve(cudaStream_t st, const DctTables &tb, int Nt, int Ny, int Nx,
 }
 
 // x and y transforms of `nplanes` planes (forward: DCT-II, inverse: DCT-III); tmp: nplanes*Ny*Nx doubles, in != out != tmp.
-// tb.split (Nx and Ny multiples of 4): even / odd folded transforms, half the flops; the spectrum then lives in the
-// permuted order "even frequencies, then odd frequencies" along x and y (tb.lam_xp / lam_yp are permuted alike; nothing
-// but the pointwise t solve ever looks at the spectrum).
+// tb.split (Nx and Ny multiples of 4): even / odd folded transforms, half the flops (3/8 along an axis whose length is a
+// multiple of 8: tb.lx / tb.ly = 2); the spectrum then lives in a permuted order along x and y (tb.lam_xp / lam_yp are permuted
+// alike; nothing but the pointwise t solve ever looks at the spectrum).
 int launch_dct_xy(cudaStream_t st, const DctTables &tb, int nplanes, int Ny, int Nx, const double *in, double *out,
                   double *tmp, int inverse)
 {
@@ -330,25 +390,67 @@ int launch_dct_xy(cudaStream_t st, const DctTables &tb, int nplanes, int Ny, int
         CUDA_TRY(cudaGetLastError());
         return FOTO_OK;
     }
-    const int hx = Nx / 2, hy = Ny / 2, R = nplanes * Ny;
+    const int hx = Nx / 2, hy = Ny / 2, qx = Nx / 4, qy = Ny / 4, R = nplanes * Ny;
     const size_t half = (size_t)nplanes * P / 2;          // elements of one folded half-volume
-    const long long hyNx = (long long)hy * Nx;
+    const size_t quarter = half / 2;
+    const long long hyNx = (long long)hy * Nx, qyNx = (long long)qy * Nx;
+    // forward x: rows of `src` -> spectrum columns of `dst` (ld Nx); the folded rows live in tmp
+    auto fwd_x = [&](const double *src, double *dst) -> int {
+        if (tb.lx == 2) {
+            k_fold2<<<fold_blocks(half), 256, 0, st>>>(half, Nx, 1, src, tmp, (size_t)R);           // tmp = [e2 | o2 | o1]: R x qx, R x qx, R x hx
+            FOTO_TRY(gemm(st, R, qx, qx, tmp, qx, tb.E2xT, qx, dst, Nx, GemmBatch{2, (long long)R * qx, 0, (long long)qx * qx, 0, qx, 0}, 2));
+            FOTO_TRY(gemm(st, R, hx, hx, tmp + 2 * (size_t)R * qx, hx, tb.ExT + (size_t)hx * hx, hx, dst + hx, Nx, one, 1));
+        } else {
+            k_fold<<<fold_blocks(half), 256, 0, st>>>(half, Nx, 1, src, tmp, half);                 // tmp = [b][R][hx]
+            FOTO_TRY(gemm(st, R, hx, hx, tmp, hx, tb.ExT, hx, dst, Nx, GemmBatch{2, (long long)R * hx, 0, (long long)hx * hx, 0, hx, 0}, 2));
+        }
+        return FOTO_OK;
+    };
+    auto fwd_y = [&](const double *src, double *dst) -> int {
+        if (tb.ly == 2) {
+            k_fold2<<<fold_blocks(half), 256, 0, st>>>(half, Ny, Nx, src, tmp, (size_t)nplanes);    // tmp = [e2 | o2 | o1][plane][rows][Nx]
+            FOTO_TRY(gemm(st, qy, Nx, qy, tb.E2y, qy, tmp, Nx, dst, Nx,
+                          GemmBatch{2, (long long)qy * qy, 0, (long long)nplanes * qyNx, qyNx, qyNx, P}, 2 * nplanes));
+            FOTO_TRY(gemm(st, hy, Nx, hy, tb.Ey + (size_t)hy * hy, hy, tmp + 2 * (size_t)nplanes * qyNx, Nx, dst + hyNx, Nx,
+                          GemmBatch{1, 0, 0, 0, hyNx, 0, P}, nplanes));
+        } else {
+            k_fold<<<fold_blocks(half), 256, 0, st>>>(half, Ny, Nx, src, tmp, half);                // tmp = [b][plane][hy][Nx]
+            FOTO_TRY(gemm(st, hy, Nx, hy, tb.Ey, hy, tmp, Nx, dst, Nx,
+                          GemmBatch{2, (long long)hy * hy, 0, (long long)nplanes * hyNx, hyNx, hyNx, P}, 2 * nplanes));
+        }
+        return FOTO_OK;
+    };
+    auto inv_y = [&](const double *src, double *dst) -> int {
+        if (tb.ly == 2) {
+            FOTO_TRY(gemm(st, qy, Nx, qy, tb.E2yT, qy, src, Nx, tmp, Nx,
+                          GemmBatch{2, (long long)qy * qy, 0, qyNx, P, (long long)nplanes * qyNx, qyNx}, 2 * nplanes));
+            FOTO_TRY(gemm(st, hy, Nx, hy, tb.EyT + (size_t)hy * hy, hy, src + hyNx, Nx, tmp + 2 * (size_t)nplanes * qyNx, Nx,
+                          GemmBatch{1, 0, 0, 0, P, 0, hyNx}, nplanes));
+            k_unfold2<<<fold_blocks(quarter), 256, 0, st>>>(quarter, Ny, Nx, tmp, dst, (size_t)nplanes);
+        } else {
+            FOTO_TRY(gemm(st, hy, Nx, hy, tb.EyT, hy, src, Nx, tmp, Nx,
+                          GemmBatch{2, (long long)hy * hy, 0, hyNx, P, (long long)nplanes * hyNx, hyNx}, 2 * nplanes));
+            k_unfold<<<fold_blocks(half), 256, 0, st>>>(half, Ny, Nx, tmp, half, dst);
+        }
+        return FOTO_OK;
+    };
+    auto inv_x = [&](const double *src, double *dst) -> int {
+        if (tb.lx == 2) {
+            FOTO_TRY(gemm(st, R, qx, qx, src, Nx, tb.E2x, qx, tmp, qx, GemmBatch{2, qx, 0, (long long)qx * qx, 0, (long long)R * qx, 0}, 2));
+            FOTO_TRY(gemm(st, R, hx, hx, src + hx, Nx, tb.Ex + (size_t)hx * hx, hx, tmp + 2 * (size_t)R * qx, hx, one, 1));
+            k_unfold2<<<fold_blocks(quarter), 256, 0, st>>>(quarter, Nx, 1, tmp, dst, (size_t)R);
+        } else {
+            FOTO_TRY(gemm(st, R, hx, hx, src, Nx, tb.Ex, hx, tmp, hx, GemmBatch{2, hx, 0, (long long)hx * hx, 0, (long long)R * hx, 0}, 2));
+            k_unfold<<<fold_blocks(half), 256, 0, st>>>(half, Nx, 1, tmp, half, dst);
+        }
+        return FOTO_OK;
+    };
     if (!inverse) {
-        // x: fold -> tmp = [b][R][hx];  out[r][b hx + j] = sum_n tmp[b][r][n] Cx[2j+b][n]
-        k_fold<<<fold_blocks(half), 256, 0, st>>>(half, Nx, 1, in, tmp, half);
-        FOTO_TRY(gemm(st, R, hx, hx, tmp, hx, tb.ExT, hx, out, Nx, GemmBatch{2, (long long)R * hx, 0, (long long)hx * hx, 0, hx, 0}, 2));
-        // y: fold -> tmp = [b][plane][hy][Nx];  out[plane][b hy + j][x] = sum_y Cy[2j+b][y] tmp[b][plane][y][x]
-        k_fold<<<fold_blocks(half), 256, 0, st>>>(half, Ny, Nx, out, tmp, half);
-        FOTO_TRY(gemm(st, hy, Nx, hy, tb.Ey, hy, tmp, Nx, out, Nx,
-                      GemmBatch{2, (long long)hy * hy, 0, (long long)nplanes * hyNx, hyNx, hyNx, P}, 2 * nplanes));
+        FOTO_TRY(fwd_x(in, out));
+        FOTO_TRY(fwd_y(out, out));                        // the y fold reads `out` into tmp before the GEMMs overwrite it
     } else {
-        // y: tmp[b][plane][y][x] = sum_j Cy[2j+b][y] in[plane][b hy + j][x];  unfold -> out
-        FOTO_TRY(gemm(st, hy, Nx, hy, tb.EyT, hy, in, Nx, tmp, Nx,
-                      GemmBatch{2, (long long)hy * hy, 0, hyNx, P, (long long)nplanes * hyNx, hyNx}, 2 * nplanes));
-        k_unfold<<<fold_blocks(half), 256, 0, st>>>(half, Ny, Nx, tmp, half, out);
-        // x: tmp[b][r][n] = sum_j out[r][b hx + j] Cx[2j+b][n];  unfold -> out
-        FOTO_TRY(gemm(st, R, hx, hx, out, Nx, tb.Ex, hx, tmp, hx, GemmBatch{2, hx, 0, (long long)hx * hx, 0, (long long)R * hx, 0}, 2));
-        k_unfold<<<fold_blocks(half), 256, 0, st>>>(half, Nx, 1, tmp, half, out);
+        FOTO_TRY(inv_y(in, out));
+        FOTO_TRY(inv_x(out, out));                        // the x GEMMs read `out` into tmp before the unfold overwrites it
     }
     CUDA_TRY(cudaGetLastError());
     return FOTO_OK;

@@ -114,7 +114,12 @@ struct DctTables {              // device pointers, owned by the context, valid 
     // the same for y, and the eigenvalues in the permuted spectrum order (even frequencies, then odd)
     bool split = false;
     double *Ex = nullptr, *ExT = nullptr, *Ey = nullptr, *EyT = nullptr, *lam_xp = nullptr, *lam_yp = nullptr;
+    // second folding level of an axis whose length is a multiple of 8 (lx / ly = 2): E2x[c][m][i] = Cx[4m+2c][i], i < Nx/4
+    int lx = 1, ly = 1;
+    double *E2x = nullptr, *E2xT = nullptr, *E2y = nullptr, *E2yT = nullptr;
 };
+void dct_host_folded2(int n, const std::vector<double> &C, const std::vector<double> &lam, std::vector<double> &E2,
+                      std::vector<double> &E2T, std::vector<double> &lam_p2);
 void dct_host_folded(int n, const std::vector<double> &C, const std::vector<double> &lam, std::vector<double> &E,
                      std::vector<double> &ET, std::vector<double> &lam_p);
 void dct_host_tables(int n, std::vector<double> &C, std::vector<double> &Ct, std::vector<double> &lam);

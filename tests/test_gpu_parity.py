@@ -354,18 +354,20 @@ def test_stepA_dct_exact_solves_the_system(tag):
 @pytest.mark.parametrize("h,w,Nt", [(48, 64, 5), (388, 584, 4), (132, 260, 3)])
 def test_dct_folded_transforms_equal_dense(h, w, Nt, monkeypatch):
     """Nx, Ny multiples of 4: the x and y transforms use the even / odd symmetry of the DCT matrix (half the flops, spectrum
-    in permuted order).  Same Poisson solution as the dense transforms (FOTO_DCT_DENSE=1) to rounding."""
+    in permuted order), twice along axes whose length is a multiple of 8 (FOTO_DCT_LEVELS).  Same Poisson solution as the dense
+    transforms (FOTO_DCT_DENSE=1) to rounding."""
     rng = np.random.default_rng(h * w)
     N = Nt * h * w
     mu, q = rng.standard_normal(3 * N), rng.standard_normal(3 * N)
     rho0, rhoT = rng.random(h * w), rng.random(h * w)
     res = {}
-    for dense in ("1", None):
+    for dense, levels in (("1", "1"), (None, "1"), (None, "2")):      # dense, one folding level, two (axes of length 8k)
         if dense: monkeypatch.setenv("FOTO_DCT_DENSE", dense)
         else: monkeypatch.delenv("FOTO_DCT_DENSE", raising=False)
-        res[dense] = foto_b200.stepA(mu, q, rho0, rhoT, 1.0, 1e-3, Nt, w, h, backend=foto_b200.POISSON_DCT_EXACT)[0]
-    assert relerr(res[None], res["1"]) < 1e-13
-    phi = res[None]
+        monkeypatch.setenv("FOTO_DCT_LEVELS", levels)
+        res[(dense, levels)] = foto_b200.stepA(mu, q, rho0, rhoT, 1.0, 1e-3, Nt, w, h, backend=foto_b200.POISSON_DCT_EXACT)[0]
+    assert relerr(res[(None, "1")], res[("1", "1")]) < 1e-13 and relerr(res[(None, "2")], res[("1", "1")]) < 1e-13
+    phi = res[(None, "2")]
     L = foto_b200.op_apply("laplacian_st", "N", Nt, w, h, 1, 1, 1, phi)
     F = foto_b200.rhs(mu, q, rho0, rhoT, 1.0, Nt, w, h)
     assert np.linalg.norm((-L + 1e-3 * phi) - F) < 1e-11 * np.linalg.norm(F)

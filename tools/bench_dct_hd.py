@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """dct_exact Poisson solve at HD size: ms per solve (CUDA events around the K2b launches) after a warm-up that builds
-the tables.  Usage: bench_dct_hd.py [h w Nt [iters]]   (env FOTO_DCT_DENSE=1: dense transforms instead of the folded ones)"""
+the tables.  Usage: bench_dct_hd.py [h w Nt [iters]]   (env FOTO_DCT_DENSE=1: dense transforms instead of the folded ones; FOTO_DCT_LEVELS=1|2: folding levels)"""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "optical-flow-optimal-transport_b200"))
@@ -20,7 +20,7 @@ info = ctx.solve_dev(d0.data_ptr(), d1.data_ptr(), Nt, w, h, *[t.data_ptr() for 
 ctx.event_record(1)
 ms = ctx.event_elapsed_ms(); st = ctx.stats()
 flop_dense = 4.0 * (w + h) * Nt * h * w          # 2 transforms each way, 2 n flop per element and axis
-print(json.dumps({"grid": [Nt, h, w], "variant": {k: os.environ.get(k) for k in ("FOTO_DCT_DENSE",)},
+print(json.dumps({"grid": [Nt, h, w], "variant": {k: os.environ.get(k) for k in ("FOTO_DCT_DENSE", "FOTO_DCT_LEVELS")},
                   "outer": info["n_outer"], "ms_per_outer": ms / info["n_outer"], "poisson_ms_per_solve": st["cg_ms"] / st["cg_launches"],
                   "rhs_ms": st["rhs_ms"] / st["cg_launches"], "prox_ms": st["prox_ms"] / st["cg_launches"],
                   "dense_equivalent_TFLOPs": flop_dense / (st["cg_ms"] / st["cg_launches"] * 1e-3) / 1e12,
