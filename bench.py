@@ -44,6 +44,7 @@ CG_KERNEL_NAMES = {0: "cg_stream_kernel", 3: "cg_fused_kernel"}   # foto_stats.c
 CG_BYTES_PER_CELL_ITER = 88      # 11 fp64 words per cell per CG iteration
 RHS_BYTES_PER_CELL = 56
 PROX_BYTES_PER_CELL = 80
+FLUSH_EVERY = 4                  # solves between two L2 flushes (512 MB memset)
 REFERENCE_BUDGET_S = 300.0       # wall budget of the timed steps of --impl reference (full solves, ~65 s per step)
 
 
@@ -200,12 +201,17 @@ def run_b200(args):
         ctx.set_cg_variant(args.cg_variant)
 
     # the whole batch is resident on every GPU (pinned host copy + HBM copy) before any timed region
-    pairs = [synth.make_pair(H, W, seed=pair_seed(r, i)) for r in range(world) for i in range(B)]
+    # (every rank synthesises its own B pairs; the others arrive by one all-gather, untimed)
     h0 = torch.empty((NB, P), dtype=torch.float64).pin_memory()
     h1 = torch.empty((NB, P), dtype=torch.float64).pin_memory()
-    for i, (a, b) in enumerate(pairs):
-        h0[i] = torch.from_numpy(a); h1[i] = torch.from_numpy(b)
+    for i in range(B):
+        a, b = synth.make_pair(H, W, seed=pair_seed(rank, i))
+        h0[rank * B + i] = torch.from_numpy(a); h1[rank * B + i] = torch.from_numpy(b)
     d0, d1 = h0.to(dev), h1.to(dev)
+    if world > 1:
+        for d, h in ((d0, h0), (d1, h1)):
+            dist.all_gather_into_tensor(d, d[rank * B:(rank + 1) * B].clone())
+            h.copy_(d)
     du, dv, dm = (torch.empty((NB, P), dtype=torch.float64, device=dev) for _ in range(3))
     hu, hv, hm = (torch.empty((NB, P), dtype=torch.float64).pin_memory() for _ in range(3))
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
@@ -221,7 +227,7 @@ def run_b200(args):
     qn = [0]
 
     def run_steps(n_steps, solve_one):
-        """n_steps passes over the batch, pairs drawn from the shared queue; L2 flushed after every B solves of this rank."""
+        """n_steps passes over the batch, pairs drawn from the shared queue; L2 flushed after every FLUSH_EVERY solves of this rank."""
         qn[0] += 1
         q = shard.WorkQueue(f"bench{qn[0]}", n_steps * NB)
         done = 0
@@ -231,7 +237,7 @@ def run_b200(args):
                 break
             solve_one(i % NB)
             done += 1
-            if done % B == 0:
+            if done % FLUSH_EVERY == 0:
                 l2_flush()
         return done
 
@@ -353,7 +359,7 @@ def run_b200(args):
                        "cg_variant": {0: "streaming (textbook recurrences)",
                                       3: "on-chip single-reduction (Chronopoulos-Gear arrangement)"}.get(stats["cg_variant"], "?"),
                        "sharding": "by pair, one shared work queue over all ranks (no data-path collective)",
-                       "l2": "512 MB device memset after every pairs_per_gpu solves (working set 87 MB/pair < 126 MB L2)",
+                       "l2": f"512 MB device memset after every {FLUSH_EVERY} solves (working set 87 MB/pair < 126 MB L2)",
                        "outer_iterations_per_pair": tot_outer / max(total_pairs, 1)},
             "outer_iters_per_s": tot_outer / (dev_ms / 1e3),
             "cg_iters_per_s": tot_cg / (dev_ms / 1e3),
@@ -437,7 +443,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs-per-gpu", type=int, default=4)
+    ap.add_argument("--pairs-per-gpu", type=int, default=16,
+                    help="pairs per GPU per step; 16 keeps the end-of-queue idle time (at most one solve, 28 ms) near 1 %% of a 5-step run")
     ap.add_argument("--cg-variant", type=int, default=None, help="-1 auto, 0 streaming, 2 on-chip single-reduction")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hd", action="store_true", help="skip the 1080x1920x16 streaming-roofline measurement")
