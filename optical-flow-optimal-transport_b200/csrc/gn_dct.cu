@@ -464,6 +464,9 @@ __global__ void __launch_bounds__(256) k_copy_out(unsigned int n, const double *
 // tile choice: FOTO_GN_TILE = 0 (64 x 64, default), 1 (128 x 128), 2 (128 x 64).  Measured at 388x584 (B200, us per GEMM,
 // X / Y transform): 64x64 15.0 / 11.1, 128x128 22.7 / 16.4, 128x64 slower than 64x64 too: the legacy mma.sync TF32 path
 // delivers ~450 FLOP/clk/SM here, so fewer, larger CTAs (50 on 148 SMs) lose more than the halved L2 traffic gains.
+// Splitting the 32-deep k-tile of a 64 x 64 block over two / four groups of warps (256 / 512 threads, accumulators added through
+// shared memory) does not help either: 84.6 -> 92.2 / 97.1 us per PCG iteration at 388x584, 94.5 -> 99.3 / 107.5 at 480x640
+// (profiles/r2_gn_ksplit.log) -- the kernel is not short of warps, it waits for its operands.
 int tile_mode(int, int)
 {
     static int forced = -2;
