@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(256) k_copy_out(unsigned int n, const double *
 // delivers ~450 FLOP/clk/SM here, so fewer, larger CTAs (50 on 148 SMs) lose more than the halved L2 traffic gains.
 // Splitting the 32-deep k-tile of a 64 x 64 block over two / four groups of warps (256 / 512 threads, accumulators added through
 // shared memory) does not help either: 84.6 -> 92.2 / 97.1 us per PCG iteration at 388x584, 94.5 -> 99.3 / 107.5 at 480x640
-// (profiles/r2_gn_ksplit.log) -- the kernel is not short of warps, it waits for its operands.
+// (profiles/r2_gn_ksplit.log); 32 x 64 and 64 x 32 tiles (370 CTAs, 2.5 per SM): 84.8 / 89.0 at 388x584, 107.0 / 107.7 at 480x640.
 int tile_mode(int, int)
 {
     static int forced = -2;
