@@ -81,15 +81,15 @@ def test_config3_sequence_vs_oracle(seq):
 @pytest.mark.parametrize("rank", range(8))
 def test_bench_seed_pairs_vs_oracle(rank):
     import bench
-    g = _golden_or_skip("bench_seeds_oracle")
+    g, g16 = _golden_or_skip("bench_seeds_oracle"), _golden_or_skip("bench_seeds_oracle_b16")      # pairs 0-3 / 4-15 of every rank
     foto_b200.set_default_cg_variant(-1)
-    for i in range(4):
+    for i in range(16):
         f0, f1 = synth.make_pair(bench.H, bench.W, seed=bench.pair_seed(rank, i))
-        _compare(g, f"rank{rank}/pair{i}", f0, f1, bench.H, bench.W, dict(bench.PARAMS))
+        _compare(g if i < 4 else g16, f"rank{rank}/pair{i}", f0, f1, bench.H, bench.W, dict(bench.PARAMS))
 
 
 def test_bench_seed_pairs_streaming_kernel_vs_oracle():
-    """The textbook-recurrence streaming kernel on two of the bench pairs (the on-chip kernel covers all 32 above)."""
+    """The textbook-recurrence streaming kernel on two of the bench pairs (the on-chip kernel covers all 128 above)."""
     import bench
     g = _golden_or_skip("bench_seeds_oracle")
     foto_b200.set_default_cg_variant(0)
