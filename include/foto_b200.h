@@ -76,7 +76,7 @@ typedef struct foto_stats {
     long long gn_launches, gn_iterations, gn_pixels;   /* GN persistent PCG kernel       */
     double    gn_ms;
     int       cg_variant;      /* last Poisson solve: 0 streaming, 2 dct_exact, 3 on-chip single-reduction */
-    int       reserved;
+    int       prox_variant;    /* last stepB/stepC launch (K3): 0 register-marching kernel, 1 TMA-staged kernel */
 } foto_stats;
 
 const char *foto_last_error(void);

@@ -433,7 +433,7 @@ extern "C" int foto_solve_dev(foto_ctx *c, const double *d_rho0, const double *d
         prof_end(c);
         FOTO_TRY(run_cg(c, d, F, phi, work, r, eps, backend));                 // stepA, Poisson solve
         prof_begin(c, CAT_PROX);
-        int blocks = launch_prox_dual(c->stream, d, phi, mu, q, r, c->prox_partials, kProxMaxBlocks, c->num_sms);   // stepB + stepC
+        int blocks = launch_prox_dual(c->stream, d, phi, mu, q, r, c->prox_partials, kProxMaxBlocks, c->num_sms, &c->stats.prox_variant);   // stepB + stepC
         if (blocks < 0) return FOTO_ERR_CUDA;
         launch_outer_decide(c->stream, c->prox_partials, blocks, c->d_res->crit, &c->d_res->cg_iters, &c->d_res->outer, tr,
                             it, tol, max_it);
@@ -1091,7 +1091,7 @@ extern "C" int foto_slab_prox_dev(foto_ctx *c, const double *phi, double *mu, do
     Dims d;
     FOTO_TRY(slab_dims(gNt, n0, nloc, Nx, Ny, cs, &d));
     FOTO_TRY(ctx_bind(c));
-    const int blocks = launch_prox_dual(c->stream, d, phi, mu, q, r, c->prox_partials, kProxMaxBlocks, c->num_sms);
+    const int blocks = launch_prox_dual(c->stream, d, phi, mu, q, r, c->prox_partials, kProxMaxBlocks, c->num_sms, &c->stats.prox_variant);
     if (blocks < 0) return FOTO_ERR_CUDA;
     launch_crit_final(c->stream, c->prox_partials, blocks, d_out2);
     c->stats.launches += 2;

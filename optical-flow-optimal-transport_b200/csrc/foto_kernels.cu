@@ -330,13 +330,15 @@ void launch_rhs(cudaStream_t st, Dims d, const double *mu, const double *q, cons
 }
 
 int launch_prox_dual(cudaStream_t st, Dims d, const double *phi, double *mu, double *q, double r, double *partials,
-                     int max_blocks, int num_sms)
+                     int max_blocks, int num_sms, int *variant)
 {
     if (prox_tma_eligible(d, phi, mu, q)) {              // TMA-staged variant (prox_tma.cu): whole volumes, even Nx
         int blocks = 0;
+        if (variant) *variant = 1;
         if (launch_prox_dual_tma(st, d, phi, mu, q, r, partials, max_blocks, num_sms, &blocks) == FOTO_OK) return blocks;
         return -1;
     }
+    if (variant) *variant = 0;
     int blocks = blocks_for(d.P, max_blocks);
     k_prox_dual<<<blocks, kThreads, 0, st>>>(d, phi, mu, q, r, 1.0 / r, partials);
     return blocks;

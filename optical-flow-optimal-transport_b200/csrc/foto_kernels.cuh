@@ -36,7 +36,7 @@ void launch_rhs(cudaStream_t st, Dims d, const double *mu, const double *q, cons
 // partials: 2*blocks doubles; returns the number of blocks used.
 // Returns the number of blocks used (= partial-sum pairs written), or -1 on a launch error (foto_last_error).
 int launch_prox_dual(cudaStream_t st, Dims d, const double *phi, double *mu, double *q, double r,
-                     double *partials, int max_blocks, int num_sms);
+                     double *partials, int max_blocks, int num_sms, int *variant = nullptr);   // variant: 0 register-marching, 1 TMA
 // TMA-staged K3 (prox_tma.cu)
 bool prox_tma_eligible(const Dims &d, const double *phi, const double *mu, const double *q);
 int launch_prox_dual_tma(cudaStream_t st, Dims d, const double *phi, double *mu, double *q, double r, double *partials,

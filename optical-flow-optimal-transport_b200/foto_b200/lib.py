@@ -46,10 +46,10 @@ class Stats(C.Structure):
                 ("cg_cells", C.c_longlong), ("cg_ms", C.c_double), ("rhs_ms", C.c_double),
                 ("prox_ms", C.c_double), ("flow_ms", C.c_double), ("rhs_cells", C.c_longlong),
                 ("prox_cells", C.c_longlong), ("gn_launches", C.c_longlong), ("gn_iterations", C.c_longlong),
-                ("gn_pixels", C.c_longlong), ("gn_ms", C.c_double), ("cg_variant", C.c_int), ("reserved", C.c_int)]
+                ("gn_pixels", C.c_longlong), ("gn_ms", C.c_double), ("cg_variant", C.c_int), ("prox_variant", C.c_int)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 _lib = None
