@@ -61,9 +61,11 @@ __device__ __forceinline__ double dw_acc(double s, const double *__restrict__ mu
 
 // Measured and rejected (same-box A/B at 1080x1920x16, this kernel: 0.772 of the HBM peak): the 256 threads of a block as an
 // 8 x 32 or 4 x 64 tile (rows y-1, y+1 from L1 instead of L2) 0.72-0.74; stencil points and weights as per-column constants with
-// two planes per trip 0.753, one 0.63, four 0.62; a thread owning a strip of four rows with the y taps from one register window of six rows
-// (L2 requests for that component 1.5 instead of 2 per cell; bit-identical F) 0.51 (profiles/r2_k1_rows.log).  A grid-stride kernel that only reads six streams and writes one reaches 1.03 of
-// the copy peak (tools/ubench_streams.cu), so the remaining gap is this kernel's halo re-reads through L2 (70 B per cell from L2).
+// two planes per trip 0.753, one 0.63, four 0.62; a thread owning a strip of four rows with the y taps from one register
+// window of six rows (1.5 instead of 2 requests per cell for that component, bit-identical F) 0.51 (profiles/r2_k1_rows.log).
+// A grid-stride kernel that only reads six streams and writes one reaches 1.03 of the copy peak (tools/ubench_streams.cu);
+// this kernel pulls 70 B per cell through L2 for its halo taps on top of the 56 B of HBM traffic, but neither variant that
+// cuts those requests (tiles, row strips) came out ahead: every one of them gives up the one-row-per-block access order.
 // One thread per (y, x) column marching through t: w_t = (mu - r q)_rho of the planes n-1, n, n+1
 // stays in registers, so every word of mu and q is read once from HBM even when a plane (16 MB at
 // 1080x1920) is far larger than what L2 keeps between two visits.
