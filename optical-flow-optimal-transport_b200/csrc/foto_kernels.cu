@@ -65,7 +65,9 @@ __device__ __forceinline__ double dw_acc(double s, const double *__restrict__ mu
 // window of six rows (1.5 instead of 2 requests per cell for that component, bit-identical F) 0.51 (profiles/r2_k1_rows.log).
 // A grid-stride kernel that only reads six streams and writes one reaches 1.03 of the copy peak (tools/ubench_streams.cu);
 // this kernel pulls 70 B per cell through L2 for its halo taps on top of the 56 B of HBM traffic, but neither variant that
-// cuts those requests (tiles, row strips) came out ahead: every one of them gives up the one-row-per-block access order.
+// cuts those requests (tiles, row strips) came out ahead.  The kernel lives on threads in flight: with 6 / 5 / 4 instead of 8
+// resident blocks per SM (40 / 48 / 52 registers, no spills instead of 60 bytes) it drops to 0.737 / 0.690 / 0.611
+// (profiles/r2_k1_rows.log) -- what K3 gained from TMA staging (loads that cost no registers) is the step left for K1.
 // One thread per (y, x) column marching through t: w_t = (mu - r q)_rho of the planes n-1, n, n+1
 // stays in registers, so every word of mu and q is read once from HBM even when a plane (16 MB at
 // 1080x1920) is far larger than what L2 keeps between two visits.
