@@ -69,7 +69,8 @@ __device__ __forceinline__ double dw_acc(double s, const double *__restrict__ mu
 // resident blocks per SM (40 / 48 / 52 registers, no spills instead of 60 bytes) it drops to 0.737 / 0.690 / 0.611
 // (profiles/r2_k1_rows.log), yet it is not waiting for DRAM latency either: prefetch.global.L2 of the taps 1 / 2 / 3 planes
 // ahead (one request per 128-byte line) costs 0.690 / 0.668 / 0.626 -- extra requests hurt, so the limit is the request rate
-// through L1 / L2 (10 loads per cell for 6 new words), which only staging the tiles once (TMA, as K3 does) would lower.
+// through L1 / L2 (10 loads per cell for 6 new words).  Taking the x taps from the neighbouring lanes by warp shuffle (8.1 loads
+// per cell, bit-identical F) costs more than it saves: 0.70.  What is left is staging the tiles once (TMA, as K3 does).
 // One thread per (y, x) column marching through t: w_t = (mu - r q)_rho of the planes n-1, n, n+1
 // stays in registers, so every word of mu and q is read once from HBM even when a plane (16 MB at
 // 1080x1920) is far larger than what L2 keeps between two visits.
